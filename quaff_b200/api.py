@@ -1,0 +1,328 @@
+"""ctypes binding of libquaffgpu.so (include/quaffgpu.h) and the host-side mirror of the reference's
+three driver seams (QuaffAligner::align, QuaffOverlapAligner::align, QuaffTrainer::getCounts).
+
+There is no CPU path: if the CUDA library is missing or no device is visible, construction raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from .params import QuaffNullParams, QuaffParams
+from .seqs import FastSeq
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+DEFAULT_LIB = os.path.join(HERE, "libquaffgpu.so")
+
+QG_REFS, QG_READS = 0, 1
+NQ, NQ1 = 94, 95
+OP_MATCH, OP_INSERT, OP_DELETE = 0, 1, 2
+ERR_NAMES = {1: "QG_ERR_CUDA", 2: "QG_ERR_INVALID", 3: "QG_ERR_UNSUPPORTED", 4: "QG_ERR_NO_DEVICE", 5: "QG_ERR_STATE", 6: "QG_ERR_PRECONDITION"}
+
+c_double_p = C.POINTER(C.c_double)
+c_u8_p = C.POINTER(C.c_uint8)
+c_u32_p = C.POINTER(C.c_uint32)
+c_u64_p = C.POINTER(C.c_uint64)
+
+# every symbol include/quaffgpu.h declares (checked by tests/test_abi.py against the header text)
+ABI_SYMBOLS = [
+    "qg_counts_size", "qg_create", "qg_destroy", "qg_last_error", "qg_free", "qg_abi_version", "qg_set_seqs",
+    "qg_set_align_model", "qg_scores_from_params", "qg_null_loglike", "qg_envelopes", "qg_viterbi", "qg_forward",
+    "qg_backward_counts", "qg_align_reads", "qg_estep", "qg_set_overlap_model", "qg_overlap_viterbi", "qg_overlap_rows",
+    "qg_overlap_reads", "qg_get_stats",
+]
+
+
+class QuaffGpuError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"{ERR_NAMES.get(code, code)}: {msg}")
+        self.code = code
+
+
+class DPConfig(C.Structure):
+    """qg_dpconfig == the QuaffDPConfig members the DP reads (qmodel.h:280-290)."""
+    _fields_ = [("sparse", C.c_int32), ("kmer_len", C.c_int32), ("kmer_threshold", C.c_int32),
+                ("band_size", C.c_int32), ("local", C.c_int32), ("max_size", C.c_uint64)]
+
+
+def dp_config(sparse=True, kmer_len=6, kmer_threshold=14, band_size=64, local=True, max_size=0) -> DPConfig:
+    return DPConfig(int(sparse), int(kmer_len), int(kmer_threshold), int(band_size), int(local), int(max_size))
+
+
+class _AlignModel(C.Structure):
+    _fields_ = [("match_k", C.c_int32), ("gap_k", C.c_int32), ("match", c_double_p), ("insert", c_double_p),
+                ("m2m", c_double_p), ("m2i", c_double_p), ("m2d", c_double_p), ("m2e", c_double_p),
+                ("d2d", C.c_double), ("d2m", C.c_double), ("i2i", C.c_double), ("i2m", C.c_double)]
+
+
+class _Params(C.Structure):
+    _fields_ = [("match_k", C.c_int32), ("gap_k", C.c_int32), ("ref_base", C.c_double * 4),
+                ("begin_insert", c_double_p), ("begin_delete", c_double_p),
+                ("extend_insert", C.c_double), ("extend_delete", C.c_double),
+                ("insert_pqr", c_double_p), ("match_pqr", c_double_p)]
+
+
+class _OverlapModel(C.Structure):
+    _fields_ = [("match_k", C.c_int32), ("gap_k", C.c_int32), ("match", c_double_p), ("insert", c_double_p),
+                ("log_ref_base", C.c_double * 4), ("begin_insert", c_double_p), ("begin_delete", c_double_p),
+                ("extend_insert", C.c_double), ("extend_delete", C.c_double)]
+
+
+class Stats(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ("ms_seed", "ms_envelope", "ms_prep", "ms_viterbi", "ms_traceback", "ms_forward",
+                                           "ms_backward", "ms_overlap", "ms_h2d", "ms_d2h")] + \
+               [(n, C.c_uint64) for n in ("kernel_launches", "cell_updates", "kmer_hits", "trace_bytes", "fwd_store_bytes",
+                                           "n_pairs", "n_segments")]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+def _dp(a: np.ndarray):
+    return a.ctypes.data_as(c_double_p)
+
+
+@dataclass
+class AlignScores:
+    """Flat QuaffScores tables (qmodel.h:181-191)."""
+    match_k: int
+    gap_k: int
+    match: np.ndarray      # [4][4^K][95]
+    insert: np.ndarray     # [4][95]
+    m2m: np.ndarray
+    m2i: np.ndarray
+    m2d: np.ndarray
+    m2e: np.ndarray
+    d2d: float
+    d2m: float
+    i2i: float
+    i2m: float
+
+
+def load_library(path: Optional[str] = None) -> C.CDLL:
+    path = path or DEFAULT_LIB
+    if not os.path.exists(path):
+        raise QuaffGpuError(4, f"{path} not found: build it with `python -m quaff_b200.build` (nvcc, sm_100a); there is no CPU fallback")
+    L = C.CDLL(path)
+    L.qg_last_error.restype = C.c_char_p
+    L.qg_last_error.argtypes = [C.c_void_p]
+    L.qg_counts_size.restype = C.c_size_t
+    L.qg_counts_size.argtypes = [C.c_int, C.c_int]
+    L.qg_null_loglike.restype = C.c_double
+    L.qg_null_loglike.argtypes = [C.c_double, c_double_p, c_u8_p, c_u8_p, C.c_uint64]
+    L.qg_free.argtypes = [C.c_void_p]
+    L.qg_destroy.argtypes = [C.c_void_p]
+    L.qg_create.argtypes = [C.POINTER(C.c_void_p), C.c_int]
+    return L
+
+
+def scores_from_params(qp: QuaffParams, lib: Optional[C.CDLL] = None) -> AlignScores:
+    """QuaffScores (qmodel.cpp:296-325) through the library's host helper."""
+    L = lib or load_library()
+    nK, nG = qp.n_match_kmers, qp.n_gap_kmers
+    bi = np.ascontiguousarray(qp.begin_insert, dtype=np.float64)
+    bd = np.ascontiguousarray(qp.begin_delete, dtype=np.float64)
+    ipqr = np.ascontiguousarray(qp.insert_pqr()); mpqr = np.ascontiguousarray(qp.match_pqr())
+    cp = _Params(qp.match_k, qp.gap_k, (C.c_double * 4)(*qp.ref_base), _dp(bi), _dp(bd), qp.extend_insert, qp.extend_delete, _dp(ipqr), _dp(mpqr))
+    match = np.zeros((4, nK, NQ1)); insert = np.zeros((4, NQ1))
+    m2m = np.zeros(nG); m2i = np.zeros(nG); m2d = np.zeros(nG); m2e = np.zeros(nG); scal = np.zeros(4)
+    rc = L.qg_scores_from_params(C.byref(cp), _dp(match), _dp(insert), _dp(m2m), _dp(m2i), _dp(m2d), _dp(m2e), _dp(scal))
+    if rc != 0:
+        raise QuaffGpuError(rc, "qg_scores_from_params")
+    return AlignScores(qp.match_k, qp.gap_k, match, insert, m2m, m2i, m2d, m2e, float(scal[0]), float(scal[1]), float(scal[2]), float(scal[3]))
+
+
+def null_loglike(np_: QuaffNullParams, seq: FastSeq, lib: Optional[C.CDLL] = None) -> float:
+    L = lib or load_library()
+    pqr = np.ascontiguousarray(np_.pqr())
+    tok = seq.tokens(); q = seq.qual_scores()
+    return L.qg_null_loglike(np_.null_emit, _dp(pqr), tok.ctypes.data_as(c_u8_p), q.ctypes.data_as(c_u8_p) if q is not None else None, len(tok))
+
+
+def _flatten(seqs: Sequence[FastSeq], want_qual: bool):
+    lens = np.array([len(s) for s in seqs], dtype=np.uint64)
+    off = np.zeros(len(seqs) + 1, dtype=np.uint64)
+    np.cumsum(lens, out=off[1:])
+    tok = np.concatenate([s.tokens() for s in seqs]) if len(seqs) else np.zeros(0, np.uint8)
+    qual = None
+    if want_qual:
+        qual = np.concatenate([s.qual_scores() for s in seqs]) if len(seqs) else np.zeros(0, np.uint8)
+    return np.ascontiguousarray(tok, dtype=np.uint8), (None if qual is None else np.ascontiguousarray(qual, dtype=np.uint8)), off
+
+
+class QuaffGPU:
+    """One context = one GPU.  Mirrors the call sequence of the reference's drivers."""
+
+    def __init__(self, device: int = 0, lib_path: Optional[str] = None):
+        self.L = load_library(lib_path)
+        self.ctx = C.c_void_p()
+        rc = self.L.qg_create(C.byref(self.ctx), int(device))
+        if rc != 0:
+            raise QuaffGpuError(rc, (self.L.qg_last_error(None) or b"").decode())
+        self.n = [0, 0]
+        self.lens = [None, None]
+        self.match_k, self.gap_k = 1, 0
+
+    def close(self):
+        if self.ctx:
+            self.L.qg_destroy(self.ctx)
+            self.ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise QuaffGpuError(rc, (self.L.qg_last_error(self.ctx) or b"").decode())
+
+    # ---- inputs ---------------------------------------------------------------------------------
+    def set_seqs_raw(self, which: int, tok: np.ndarray, qual: Optional[np.ndarray], off: np.ndarray):
+        tok = np.ascontiguousarray(tok, dtype=np.uint8); off = np.ascontiguousarray(off, dtype=np.uint64)
+        if qual is not None:
+            qual = np.ascontiguousarray(qual, dtype=np.uint8)
+        self._check(self.L.qg_set_seqs(self.ctx, which, C.c_size_t(len(off) - 1), tok.ctypes.data_as(c_u8_p),
+                                       qual.ctypes.data_as(c_u8_p) if qual is not None else None, off.ctypes.data_as(c_u64_p)))
+        self.n[which] = len(off) - 1
+        self.lens[which] = np.diff(off).astype(np.int64)
+
+    def set_refs(self, refs: Sequence[FastSeq]):
+        tok, _, off = _flatten(refs, False)
+        self.set_seqs_raw(QG_REFS, tok, None, off)
+
+    def set_reads(self, reads: Sequence[FastSeq], use_quals: bool = True):
+        want = use_quals and all(r.has_qual() for r in reads) and len(reads) > 0
+        tok, qual, off = _flatten(reads, want)
+        self.set_seqs_raw(QG_READS, tok, qual, off)
+
+    def set_align_scores(self, s: AlignScores):
+        self._keep = s
+        m = _AlignModel(s.match_k, s.gap_k, _dp(np.ascontiguousarray(s.match)), _dp(np.ascontiguousarray(s.insert)),
+                        _dp(s.m2m), _dp(s.m2i), _dp(s.m2d), _dp(s.m2e), s.d2d, s.d2m, s.i2i, s.i2m)
+        self._check(self.L.qg_set_align_model(self.ctx, C.byref(m)))
+        self.match_k, self.gap_k = s.match_k, s.gap_k
+
+    def set_params(self, qp: QuaffParams):
+        self.set_align_scores(scores_from_params(qp, self.L))
+
+    # ---- per-object entry points --------------------------------------------------------------------
+    @staticmethod
+    def _pairs(xi, yi):
+        xi = np.ascontiguousarray(xi, dtype=np.uint32); yi = np.ascontiguousarray(yi, dtype=np.uint32)
+        assert len(xi) == len(yi)
+        return xi, yi
+
+    def envelopes(self, cfg: DPConfig, xi, yi, cell_size: int = 24, x_set: int = QG_REFS):
+        xi, yi = self._pairs(xi, yi)
+        n = len(xi)
+        d = C.POINTER(C.c_int32)(); off = np.zeros(n + 1, dtype=np.uint64); cu = np.zeros(n, dtype=np.uint64)
+        self._check(self.L.qg_envelopes(self.ctx, C.byref(cfg), C.c_uint64(cell_size), x_set, C.c_size_t(n), xi.ctypes.data_as(c_u32_p),
+                                        yi.ctypes.data_as(c_u32_p), C.byref(d), off.ctypes.data_as(c_u64_p), cu.ctypes.data_as(c_u64_p)))
+        total = int(off[n])
+        flat = np.ctypeslib.as_array(d, shape=(max(total, 1),))[:total].copy()
+        self.L.qg_free(d)
+        return [flat[int(off[p]):int(off[p + 1])] for p in range(n)], cu
+
+    def _take_paths(self, ptr, off, n):
+        total = int(off[n])
+        flat = np.ctypeslib.as_array(ptr, shape=(max(total, 1),))[:total].copy() if ptr else np.zeros(0, np.uint8)
+        if ptr:
+            self.L.qg_free(ptr)
+        return [flat[int(off[p]):int(off[p + 1])] for p in range(n)]
+
+    def viterbi(self, cfg: DPConfig, xi, yi, want_path=None):
+        xi, yi = self._pairs(xi, yi)
+        n = len(xi)
+        score = np.zeros(n); xs = np.zeros(n, np.uint32); xe = np.zeros(n, np.uint32)
+        path = c_u8_p(); off = np.zeros(n + 1, dtype=np.uint64)
+        wp = None if want_path is None else np.ascontiguousarray(want_path, dtype=np.uint8)
+        self._check(self.L.qg_viterbi(self.ctx, C.byref(cfg), C.c_size_t(n), xi.ctypes.data_as(c_u32_p), yi.ctypes.data_as(c_u32_p),
+                                      wp.ctypes.data_as(c_u8_p) if wp is not None else None, _dp(score), xs.ctypes.data_as(c_u32_p),
+                                      xe.ctypes.data_as(c_u32_p), C.byref(path), off.ctypes.data_as(c_u64_p)))
+        return dict(score=score, x_start=xs, x_end=xe, paths=self._take_paths(path, off, n))
+
+    def forward(self, cfg: DPConfig, xi, yi) -> np.ndarray:
+        xi, yi = self._pairs(xi, yi)
+        ll = np.zeros(len(xi))
+        self._check(self.L.qg_forward(self.ctx, C.byref(cfg), C.c_size_t(len(xi)), xi.ctypes.data_as(c_u32_p), yi.ctypes.data_as(c_u32_p), _dp(ll)))
+        return ll
+
+    def counts_size(self) -> int:
+        return self.L.qg_counts_size(self.match_k, self.gap_k)
+
+    def backward_counts(self, cfg: DPConfig, xi, yi, weights=None, per_pair=False):
+        xi, yi = self._pairs(xi, yi)
+        n = len(xi); nc = self.counts_size()
+        f = np.zeros(n); b = np.zeros(n); csum = np.zeros(nc)
+        cpp = np.zeros((n, nc)) if per_pair else None
+        w = None if weights is None else np.ascontiguousarray(weights, dtype=np.float64)
+        self._check(self.L.qg_backward_counts(self.ctx, C.byref(cfg), C.c_size_t(n), xi.ctypes.data_as(c_u32_p), yi.ctypes.data_as(c_u32_p),
+                                              _dp(w) if w is not None else None, _dp(f), _dp(b), _dp(csum), _dp(cpp) if per_pair else None))
+        return dict(fwd=f, back=b, counts=csum, counts_per_pair=cpp)
+
+    # ---- seam A: QuaffAligner::align (qmodel.cpp:2624) -----------------------------------------------
+    def align_reads(self, cfg: DPConfig, null_ll: np.ndarray):
+        n = self.n[QG_READS]
+        null_ll = np.ascontiguousarray(null_ll, dtype=np.float64)
+        best = np.zeros(n, np.uint32); score = np.zeros(n); xs = np.zeros(n, np.uint32); xe = np.zeros(n, np.uint32)
+        path = c_u8_p(); off = np.zeros(n + 1, dtype=np.uint64)
+        self._check(self.L.qg_align_reads(self.ctx, C.byref(cfg), _dp(null_ll), best.ctypes.data_as(c_u32_p), _dp(score),
+                                          xs.ctypes.data_as(c_u32_p), xe.ctypes.data_as(c_u32_p), C.byref(path), off.ctypes.data_as(c_u64_p)))
+        return dict(best_ref=best, score=score, x_start=xs, x_end=xe, paths=self._take_paths(path, off, n))
+
+    # ---- seam C: QuaffTrainer::getCounts (qmodel.cpp:2005) --------------------------------------------
+    def estep(self, cfg: DPConfig, use_null: bool, null_ll: np.ndarray, sort_order: Optional[List[List[int]]] = None):
+        ny, nx = self.n[QG_READS], self.n[QG_REFS]
+        so = np.zeros((ny, nx), dtype=np.uint32); sl = np.zeros(ny, dtype=np.uint32)
+        for m in range(ny):
+            o = list(range(nx)) if sort_order is None else sort_order[m]
+            so[m, :len(o)] = o; sl[m] = len(o)
+        null_ll = np.ascontiguousarray(null_ll, dtype=np.float64)
+        yll = np.zeros(ny); counts = np.zeros(self.counts_size()); tot = C.c_double()
+        self._check(self.L.qg_estep(self.ctx, C.byref(cfg), int(use_null), _dp(null_ll), so.ctypes.data_as(c_u32_p), sl.ctypes.data_as(c_u32_p),
+                                    _dp(yll), _dp(counts), C.byref(tot)))
+        return dict(y_loglike=yll, counts=counts, loglike=tot.value, sort_order=[list(map(int, so[m, :sl[m]])) for m in range(ny)])
+
+    # ---- overlap ---------------------------------------------------------------------------------------
+    def set_overlap_params(self, qp: QuaffParams):
+        s = scores_from_params(qp, self.L)
+        self._okeep = (s, np.ascontiguousarray(qp.begin_insert, dtype=np.float64), np.ascontiguousarray(qp.begin_delete, dtype=np.float64))
+        m = _OverlapModel(qp.match_k, qp.gap_k, _dp(np.ascontiguousarray(s.match)), _dp(np.ascontiguousarray(s.insert)),
+                          (C.c_double * 4)(*[float(np.log(v)) for v in qp.ref_base]), _dp(self._okeep[1]), _dp(self._okeep[2]),
+                          qp.extend_insert, qp.extend_delete)
+        self._check(self.L.qg_set_overlap_model(self.ctx, C.byref(m)))
+
+    def overlap_viterbi(self, cfg: DPConfig, xi, yi, y_complemented, want_path=None):
+        xi, yi = self._pairs(xi, yi)
+        n = len(xi)
+        yc = np.ascontiguousarray(y_complemented, dtype=np.uint8)
+        wp = None if want_path is None else np.ascontiguousarray(want_path, dtype=np.uint8)
+        score = np.zeros(n); co = np.zeros((n, 4), np.uint32); path = c_u8_p(); off = np.zeros(n + 1, dtype=np.uint64)
+        self._check(self.L.qg_overlap_viterbi(self.ctx, C.byref(cfg), C.c_size_t(n), xi.ctypes.data_as(c_u32_p), yi.ctypes.data_as(c_u32_p),
+                                              yc.ctypes.data_as(c_u8_p), wp.ctypes.data_as(c_u8_p) if wp is not None else None,
+                                              _dp(score), co.ctypes.data_as(c_u32_p), C.byref(path), off.ctypes.data_as(c_u64_p)))
+        return dict(score=score, coords=co, paths=self._take_paths(path, off, n))
+
+    def overlap_rows(self, x_tok: np.ndarray, y_tok: np.ndarray, coords4: np.ndarray, path: np.ndarray) -> Tuple[str, str]:
+        x_tok = np.ascontiguousarray(x_tok, dtype=np.uint8); y_tok = np.ascontiguousarray(y_tok, dtype=np.uint8)
+        co = np.ascontiguousarray(coords4, dtype=np.uint32); path = np.ascontiguousarray(path, dtype=np.uint8)
+        xr = C.c_void_p(); yr = C.c_void_p()
+        rc = self.L.qg_overlap_rows(x_tok.ctypes.data_as(c_u8_p), y_tok.ctypes.data_as(c_u8_p), co.ctypes.data_as(c_u32_p),
+                                    path.ctypes.data_as(c_u8_p), C.c_uint64(len(path)), C.byref(xr), C.byref(yr))
+        if rc != 0:
+            raise QuaffGpuError(rc, "qg_overlap_rows")
+        a, b = C.string_at(xr.value).decode(), C.string_at(yr.value).decode()
+        self.L.qg_free(xr); self.L.qg_free(yr)
+        return a, b
+
+    # ---- instrumentation -------------------------------------------------------------------------------
+    def stats(self, reset: bool = False) -> dict:
+        st = Stats()
+        self._check(self.L.qg_get_stats(self.ctx, C.byref(st), int(reset)))
+        return st.as_dict()

@@ -1,0 +1,60 @@
+"""Build libquaffgpu.so for sm_100a with nvcc (in-tree, next to this file).
+
+`-fmad=false`: the FP64 kernels must evaluate the reference's expressions with the reference's
+rounding (no FMA contraction), which is what makes Viterbi cells/paths and Forward cells bit-identical.
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libquaffgpu.so")
+SOURCES = ["quaffgpu.cu"]
+HEADERS = ["qg_common.cuh", "qg_seed.cuh", "qg_dp.cuh", "qg_backward.cuh", "qg_overlap.cuh", "qg_host.cuh", os.path.join("..", "..", "include", "quaffgpu.h")]
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-lineinfo", "-std=c++17", "-fmad=false",
+    "--compiler-options", "-fPIC", "-shared",
+    "-Xptxas", "-v",
+]
+
+
+def nvcc_path() -> str:
+    p = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(p):
+        raise RuntimeError("nvcc not found: libquaffgpu cannot be built (there is no CPU fallback)")
+    return p
+
+
+def needs_build() -> bool:
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    for f in SOURCES + HEADERS:
+        fp = os.path.join(CSRC, f)
+        if os.path.exists(fp) and os.path.getmtime(fp) > t:
+            return True
+    return False
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and not needs_build():
+        return LIB
+    cmd = [nvcc_path()] + NVCC_FLAGS + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    log = res.stdout + res.stderr
+    with open(os.path.join(HERE, "build.log"), "w") as fh:
+        fh.write(" ".join(cmd) + "\n" + log)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + log[-4000:])
+    if verbose:
+        print(log)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force=True, verbose=True))

@@ -1,0 +1,670 @@
+// libquaffgpu: C ABI (include/quaffgpu.h) and host orchestration of the sm_100a kernels.
+// Compiled by nvcc for sm_100a (see quaff_b200/build.py).  The same translation unit also compiles
+// under g++ with -DQG_EMU against tests/emu/cuda_emu.h, which is test infrastructure only.
+#include "qg_common.cuh"
+#include "qg_seed.cuh"
+#include "qg_dp.cuh"
+#include <map>
+#include <numeric>
+
+static qg_error g_create_error;
+
+enum {
+  SC_PAIRDESC = 0, SC_ITEMS, SC_ITEMRUNS, SC_ITEMNRUNS, SC_PAIRRUNS, SC_PAIRINFO, SC_PAIRCU, SC_FLAGS,
+  SC_SEGS, SC_RPJOBS, SC_RP, SC_TRACE, SC_ENDVALS, SC_PAIRDP, SC_OUT0, SC_OUT1, SC_OUT2, SC_OUT3, SC_PATHSCR, SC_PATHOUT,
+  SC_STORE, SC_ROWACC, SC_MISC0, SC_MISC1
+};
+
+// ---- small helpers -----------------------------------------------------------------------------------
+static int qg_upload (qg_ctx* ctx, qg_dbuf& b, const void* src, size_t bytes) {
+  QG_TRY (qg_reserve (ctx, b, bytes));
+  if (bytes) QG_CUDA (ctx, cudaMemcpyAsync (b.p, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  return QG_OK;
+}
+static int qg_download (qg_ctx* ctx, void* dst, const void* src, size_t bytes) {
+  if (bytes) QG_CUDA (ctx, cudaMemcpyAsync (dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  QG_CUDA (ctx, cudaStreamSynchronize (ctx->stream));
+  return QG_OK;
+}
+static int qg_check_launch (qg_ctx* ctx, const char* what) {
+  cudaError_t e = cudaGetLastError ();
+  if (e != cudaSuccess) QG_FAIL (ctx, QG_ERR_CUDA, "launch of %s failed: %s", what, cudaGetErrorString (e));
+  ctx->stats.kernel_launches += 1;
+  return QG_OK;
+}
+struct qg_timer {
+  qg_ctx* ctx; double* acc;
+  qg_timer (qg_ctx* c, double* a) : ctx (c), acc (a) { cudaEventRecord (ctx->ev[0], ctx->stream); }
+  ~qg_timer () {
+    cudaEventRecord (ctx->ev[1], ctx->stream);
+    cudaEventSynchronize (ctx->ev[1]);
+    float ms = 0; cudaEventElapsedTime (&ms, ctx->ev[0], ctx->ev[1]);
+    *acc += ms;
+  }
+};
+static size_t qg_env_size (const char* name, size_t dflt) {
+  const char* v = getenv (name);
+  return (v && *v) ? (size_t) strtoull (v, nullptr, 10) : dflt;
+}
+
+// ---- context ---------------------------------------------------------------------------------------------
+extern "C" int qg_abi_version (void) { return 1; }
+
+extern "C" const char* qg_last_error (const qg_ctx* ctx) { return ctx ? ctx->err.msg.c_str () : g_create_error.msg.c_str (); }
+
+extern "C" void qg_free (void* p) { free (p); }
+
+extern "C" size_t qg_counts_size (int match_k, int gap_k) {
+  return 4 * (size_t) qg_pow4 (match_k) * QG_NQUAL + 4 * QG_NQUAL + 4 * (size_t) qg_pow4 (gap_k) + 4;
+}
+
+extern "C" int qg_create (qg_ctx** out, int device) {
+  if (!out) return QG_ERR_INVALID;
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount (&ndev);
+  if (e != cudaSuccess || ndev <= 0) {
+    g_create_error.code = QG_ERR_NO_DEVICE;
+    g_create_error.msg = std::string ("no CUDA device available (") + (e != cudaSuccess ? cudaGetErrorString (e) : "device count 0") +
+                         "); libquaffgpu has no CPU path";
+    return QG_ERR_NO_DEVICE;
+  }
+  if (device < 0 || device >= ndev) { g_create_error.code = QG_ERR_INVALID; g_create_error.msg = "device index out of range"; return QG_ERR_INVALID; }
+  qg_ctx* ctx = new qg_ctx ();
+  ctx->device = device;
+  memset (&ctx->stats, 0, sizeof (ctx->stats));
+  auto fail = [&] (const char* what, cudaError_t ce) {
+    g_create_error.code = QG_ERR_CUDA; g_create_error.msg = std::string (what) + ": " + cudaGetErrorString (ce);
+    delete ctx; return QG_ERR_CUDA; };
+  if ((e = cudaSetDevice (device)) != cudaSuccess) return fail ("cudaSetDevice", e);
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties (&prop, device)) != cudaSuccess) return fail ("cudaGetDeviceProperties", e);
+  ctx->sm_count = prop.multiProcessorCount;
+  ctx->smem_optin = prop.sharedMemPerBlockOptin;
+  if ((e = cudaStreamCreateWithFlags (&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail ("cudaStreamCreate", e);
+  if ((e = cudaEventCreate (&ctx->ev[0])) != cudaSuccess) return fail ("cudaEventCreate", e);
+  if ((e = cudaEventCreate (&ctx->ev[1])) != cudaSuccess) return fail ("cudaEventCreate", e);
+  // the reference's log-sum-exp table, built with the host libm exactly as logsumexp.cpp:20-28 does
+  {
+    const int n = ((int) (10 / .0001)) + 1;
+    std::vector<double> tab (n + 1);
+    for (int t = 0; t < n; ++t) { const double x = t * .0001; tab[t] = log (1. + exp (-x)); }
+    tab[n] = 0;
+    if (qg_upload (ctx, ctx->d_lse, tab.data (), sizeof (double) * (n + 1)) != QG_OK || cudaStreamSynchronize (ctx->stream) != cudaSuccess) {
+      g_create_error = ctx->err; delete ctx; return QG_ERR_CUDA; }
+  }
+  *out = ctx;
+  return QG_OK;
+}
+
+extern "C" void qg_destroy (qg_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice (ctx->device);
+  cudaStreamSynchronize (ctx->stream);
+  auto rel = [] (qg_dbuf& b) { if (b.p) cudaFree (b.p); b.p = nullptr; b.cap = 0; };
+  for (auto& s : ctx->seqs) { rel (s.d_tok); rel (s.d_qual); rel (s.d_off); rel (s.d_packed); rel (s.d_poff); rel (s.d_codes); }
+  rel (ctx->model.d_match); rel (ctx->model.d_insert); rel (ctx->model.d_gap);
+  rel (ctx->omodel.d_match); rel (ctx->omodel.d_insert); rel (ctx->omodel.d_m2m); rel (ctx->omodel.d_m2i); rel (ctx->omodel.d_m2d);
+  for (int s = 0; s < 2; ++s) { rel (ctx->omodel.d_pair[s]); rel (ctx->omodel.d_xonly[s]); rel (ctx->omodel.d_yonly[s]); rel (ctx->omodel.d_none[s]); }
+  rel (ctx->d_lse);
+  for (auto& b : ctx->scratch) rel (b);
+  cudaEventDestroy (ctx->ev[0]); cudaEventDestroy (ctx->ev[1]);
+  cudaStreamDestroy (ctx->stream);
+  delete ctx;
+}
+
+extern "C" int qg_get_stats (qg_ctx* ctx, qg_stats* out, int reset) {
+  if (!ctx || !out) return QG_ERR_INVALID;
+  *out = ctx->stats;
+  if (reset) memset (&ctx->stats, 0, sizeof (ctx->stats));
+  return QG_OK;
+}
+
+// ---- inputs ----------------------------------------------------------------------------------------------
+extern "C" int qg_set_seqs (qg_ctx* ctx, int which, size_t n, const uint8_t* tok, const uint8_t* qual, const uint64_t* offsets) {
+  if (!ctx) return QG_ERR_INVALID;
+  if (which != QG_REFS && which != QG_READS) QG_FAIL (ctx, QG_ERR_INVALID, "qg_set_seqs: unknown sequence set %d", which);
+  if (!offsets || (n && !tok)) QG_FAIL (ctx, QG_ERR_INVALID, "qg_set_seqs: null pointer");
+  if (n >= 0xFFFFFFFFull) QG_FAIL (ctx, QG_ERR_INVALID, "qg_set_seqs: too many sequences");
+  qg_seqset& s = ctx->seqs[which];
+  s.n = n;
+  s.off.assign (offsets, offsets + n + 1);
+  s.total = s.off[n] - s.off[0];
+  if (s.off[0] != 0) QG_FAIL (ctx, QG_ERR_INVALID, "qg_set_seqs: offsets[0] must be 0");
+  s.max_len = 0;
+  for (size_t i = 0; i < n; ++i) {
+    if (s.off[i + 1] < s.off[i]) QG_FAIL (ctx, QG_ERR_INVALID, "qg_set_seqs: offsets not monotone at %zu", i);
+    const uint64_t l = s.off[i + 1] - s.off[i];
+    if (l > 0x7FFFFFF0ull) QG_FAIL (ctx, QG_ERR_INVALID, "qg_set_seqs: sequence %zu too long", i);
+    s.max_len = std::max (s.max_len, (uint32_t) l);
+  }
+  for (uint64_t t = 0; t < s.total; ++t)
+    if (tok[t] > 3) QG_FAIL (ctx, QG_ERR_INVALID, "qg_set_seqs: token %u at position %llu is not in {0,1,2,3} (the reference aborts on non-ACGT, fastseq.cpp:76-79)", tok[t], (unsigned long long) t);
+  s.has_qual = qual != nullptr;
+  if (qual) for (uint64_t t = 0; t < s.total; ++t) if (qual[t] >= QG_NQUAL) QG_FAIL (ctx, QG_ERR_INVALID, "qg_set_seqs: quality score %u out of range", qual[t]);
+  s.h_tok.assign (tok, tok + s.total);
+  if (qual) s.h_qual.assign (qual, qual + s.total); else s.h_qual.clear ();
+  s.codes_k = 0;
+  // packed layout: each sequence starts on a word boundary and is followed by one zero word
+  s.poff.resize (n + 1);
+  uint64_t w = 0;
+  for (size_t i = 0; i < n; ++i) { s.poff[i] = w; w += (s.off[i + 1] - s.off[i] + 31) / 32 + 1; }
+  s.poff[n] = w;
+  {
+    qg_timer tm (ctx, &ctx->stats.ms_h2d);
+    QG_TRY (qg_upload (ctx, s.d_tok, tok, s.total));
+    if (qual) QG_TRY (qg_upload (ctx, s.d_qual, qual, s.total));
+    QG_TRY (qg_upload (ctx, s.d_off, s.off.data (), sizeof (uint64_t) * (n + 1)));
+    QG_TRY (qg_upload (ctx, s.d_poff, s.poff.data (), sizeof (uint64_t) * (n + 1)));
+    QG_TRY (qg_reserve (ctx, s.d_packed, sizeof (uint64_t) * (w + 1)));
+  }
+  if (w) {
+    qg_timer tm (ctx, &ctx->stats.ms_prep);
+    QG_LAUNCH (qg_pack_kernel, (unsigned) ((w + 255) / 256), 256, 0, ctx->stream,
+               s.d_tok.as<uint8_t> (), s.d_off.as<uint64_t> (), s.d_poff.as<uint64_t> (), (uint32_t) n, w, s.d_packed.as<uint64_t> ());
+    QG_TRY (qg_check_launch (ctx, "qg_pack_kernel"));
+  }
+  QG_CUDA (ctx, cudaStreamSynchronize (ctx->stream));
+  return QG_OK;
+}
+
+static int qg_ensure_codes (qg_ctx* ctx, int which, int k) {
+  qg_seqset& s = ctx->seqs[which];
+  if (s.codes_k == k) return QG_OK;
+  QG_TRY (qg_reserve (ctx, s.d_codes, sizeof (uint16_t) * (s.total + 1)));
+  if (s.total) {
+    qg_timer tm (ctx, &ctx->stats.ms_prep);
+    QG_LAUNCH (qg_codes_kernel, (unsigned) ((s.total + 255) / 256), 256, 0, ctx->stream,
+               s.d_tok.as<uint8_t> (), s.d_off.as<uint64_t> (), (uint32_t) s.n, s.total, k, s.d_codes.as<uint16_t> ());
+    QG_TRY (qg_check_launch (ctx, "qg_codes_kernel"));
+  }
+  s.codes_k = k;
+  return QG_OK;
+}
+
+extern "C" int qg_set_align_model (qg_ctx* ctx, const qg_align_model* m) {
+  if (!ctx || !m) return QG_ERR_INVALID;
+  if (m->match_k < 1 || m->match_k > 6 || m->gap_k < 0 || m->gap_k > 6) QG_FAIL (ctx, QG_ERR_UNSUPPORTED, "model orders K=%d G=%d outside 1..6 / 0..6", m->match_k, m->gap_k);
+  qg_model_dev& d = ctx->model;
+  d.match_k = m->match_k; d.gap_k = m->gap_k; d.nK = qg_pow4 (m->match_k); d.nG = qg_pow4 (m->gap_k);
+  QG_TRY (qg_upload (ctx, d.d_match, m->match, sizeof (double) * 4 * d.nK * QG_NQ1));
+  QG_TRY (qg_upload (ctx, d.d_insert, m->insert, sizeof (double) * 4 * QG_NQ1));
+  std::vector<double> gap (4 * d.nG);
+  for (uint64_t g = 0; g < d.nG; ++g) { gap[g] = m->m2m[g]; gap[d.nG + g] = m->m2i[g]; gap[2 * d.nG + g] = m->m2d[g]; gap[3 * d.nG + g] = m->m2e[g]; }
+  QG_TRY (qg_upload (ctx, d.d_gap, gap.data (), sizeof (double) * gap.size ()));
+  d.d2d = m->d2d; d.d2m = m->d2m; d.i2i = m->i2i; d.i2m = m->i2m;
+  QG_CUDA (ctx, cudaStreamSynchronize (ctx->stream));
+  d.set = true;
+  return QG_OK;
+}
+
+// ---- host arithmetic that the reference also does once per run on the host ---------------------------------
+static double qg_log_negbinom (int k, double p, double r) {
+  // log(gsl_ran_negative_binomial_pdf(k,p,r)), negbinom.cpp:30-32
+  const double f = lgamma (k + r), a = lgamma (r), b = lgamma (k + 1.0);
+  return log (exp (f - a - b) * pow (p, r) * pow (1 - p, (double) k));
+}
+
+extern "C" int qg_scores_from_params (const qg_params* qp, double* match, double* insert,
+                                      double* m2m, double* m2i, double* m2d, double* m2e, double* scal4) {
+  if (!qp || !match || !insert || !m2m || !m2i || !m2d || !m2e || !scal4) return QG_ERR_INVALID;
+  const uint64_t nK = qg_pow4 (qp->match_k), nG = qg_pow4 (qp->gap_k);
+  auto fill = [] (const double* pqr, double* out95) {       // SymQualScores, qmodel.cpp:87-93
+    const double lsp = log (pqr[0]);
+    for (int k = 0; k < QG_NQUAL; ++k) out95[k] = lsp + qg_log_negbinom (k, pqr[1], pqr[2]);
+    out95[QG_NQUAL] = lsp;
+  };
+  for (int i = 0; i < 4; ++i) {
+    fill (qp->insert_pqr + 3 * i, insert + i * QG_NQ1);
+    for (uint64_t j = 0; j < nK; ++j) fill (qp->match_pqr + 3 * (i * nK + j), match + (i * nK + j) * QG_NQ1);
+  }
+  for (uint64_t j = 0; j < nG; ++j) {                        // QuaffScores, qmodel.cpp:312-318
+    m2m[j] = log (1 - qp->begin_insert[j]) + log (1 - qp->begin_delete[j]);
+    m2i[j] = log (qp->begin_insert[j]);
+    m2d[j] = log (1 - qp->begin_insert[j]) + log (qp->begin_delete[j]);
+    m2e[j] = log (qp->begin_insert[j]);
+  }
+  scal4[0] = log (qp->extend_delete); scal4[1] = log (1 - qp->extend_delete);
+  scal4[2] = log (qp->extend_insert); scal4[3] = log (1 - qp->extend_insert);
+  return QG_OK;
+}
+
+extern "C" double qg_null_loglike (double null_emit, const double* null_pqr, const uint8_t* tok, const uint8_t* qual, uint64_t len) {
+  double ll = len * log (null_emit) + log (1. - null_emit);    // qmodel.cpp:1875-1890
+  for (uint64_t i = 0; i < len; ++i) {
+    const double* d = null_pqr + 3 * tok[i];
+    ll += log (d[0]);
+    if (qual) ll += qg_log_negbinom (qual[i], d[1], d[2]);
+  }
+  return ll;
+}
+
+// ---- envelope stage ------------------------------------------------------------------------------------------
+struct qg_env_result {
+  std::vector<uint32_t> run_begin;   // [n_pairs+1] into runs
+  std::vector<int2> runs;
+  std::vector<uint64_t> cu;          // [n_pairs]
+  std::vector<uint32_t> ndiag;       // [n_pairs]
+};
+
+static int qg_envelope_stage (qg_ctx* ctx, const qg_dpconfig* cfg, uint64_t cell_size, int x_set,
+                              size_t n_pairs, const uint32_t* xi, const uint32_t* yi, qg_env_result& out) {
+  (void) cell_size;
+  const qg_seqset& X = ctx->seqs[x_set];
+  const qg_seqset& Y = ctx->seqs[QG_READS];
+  const int k = cfg->kmer_len;
+  std::vector<qg_pair_desc> pd (n_pairs);
+  std::vector<qg_seed_item> items;
+  const uint32_t run_cap = (uint32_t) qg_env_size ("QG_RUN_CAP", 64);
+  bool any_sparse = false;
+  uint32_t ymax = 0;
+  uint64_t run_total = 0;
+  for (size_t p = 0; p < n_pairs; ++p) {
+    if (xi[p] >= X.n || yi[p] >= Y.n) QG_FAIL (ctx, QG_ERR_INVALID, "pair %zu: sequence index out of range", p);
+    qg_pair_desc& d = pd[p];
+    d.xseq = xi[p]; d.yseq = yi[p]; d.xlen = X.len (xi[p]); d.ylen = Y.len (yi[p]);
+    d.xoff = X.off[xi[p]]; d.yoff = Y.off[yi[p]];
+    if (d.xlen == 0 || d.ylen == 0) QG_FAIL (ctx, QG_ERR_INVALID, "pair %zu: empty sequence", p);
+    bool full = !cfg->sparse;
+    if (!full && cfg->kmer_threshold >= 0) {                    // diagenv.cpp:23-29
+      const uint32_t min_len = 2u * (uint32_t) (k + cfg->kmer_threshold);
+      if (d.xlen < min_len || d.ylen < min_len) full = true;
+    }
+    d.full = full ? 1 : 0;
+    d.item_begin = (uint32_t) items.size ();
+    if (!full) {
+      if (cfg->kmer_threshold < 0)
+        QG_FAIL (ctx, QG_ERR_UNSUPPORTED, "memory-guided seeding (-kmatchmb/-kmatchmax) is handled by qg_envelope_memory_stage");
+      if (d.xlen < (uint32_t) k || d.ylen < (uint32_t) k)
+        QG_FAIL (ctx, QG_ERR_PRECONDITION, "pair %zu: sequence shorter than k=%d (the reference's KmerIndex underflows here, fastseq.cpp:247)", p, k);
+      if (d.ylen > 65000) QG_FAIL (ctx, QG_ERR_UNSUPPORTED, "pair %zu: read of %u bases exceeds the 16-bit bucket index of the seeding kernel", p, d.ylen);
+      any_sparse = true;
+      ymax = std::max (ymax, d.ylen);
+      const int64_t dmin = -((int64_t) d.ylen - k), dmax = (int64_t) d.xlen - k;   // diagonals that can receive hits
+      for (int64_t b = dmin; b <= dmax; b += QG_SEED_CHUNK) {
+        qg_seed_item it; it.pair = (uint32_t) p; it.d_begin = (int32_t) b; it.d_end = (int32_t) std::min<int64_t> (b + QG_SEED_CHUNK, dmax + 1);
+        items.push_back (it);
+      }
+    }
+    d.item_end = (uint32_t) items.size ();
+    d.run_out = (uint32_t) run_total;
+    run_total += (uint64_t) (d.item_end - d.item_begin) * run_cap + 1;
+    if (run_total > 0xFFFFFFF0ull) QG_FAIL (ctx, QG_ERR_UNSUPPORTED, "too many seeding work items in one call; split the pair list");
+  }
+  if (any_sparse && (k < 5 || k > 7)) QG_FAIL (ctx, QG_ERR_UNSUPPORTED, "-kmatch %d: this build's seeding kernel indexes k-mers of length 5..7 in shared memory", k);
+
+  qg_dbuf &dPD = ctx->scratch[SC_PAIRDESC], &dIT = ctx->scratch[SC_ITEMS], &dIR = ctx->scratch[SC_ITEMRUNS], &dIN = ctx->scratch[SC_ITEMNRUNS];
+  qg_dbuf &dPR = ctx->scratch[SC_PAIRRUNS], &dPI = ctx->scratch[SC_PAIRINFO], &dPC = ctx->scratch[SC_PAIRCU], &dFL = ctx->scratch[SC_FLAGS];
+  QG_TRY (qg_upload (ctx, dPD, pd.data (), sizeof (qg_pair_desc) * n_pairs));
+  QG_TRY (qg_upload (ctx, dIT, items.data (), sizeof (qg_seed_item) * items.size ()));
+  QG_TRY (qg_reserve (ctx, dIR, sizeof (int2) * (items.size () * run_cap + 1)));
+  QG_TRY (qg_reserve (ctx, dIN, sizeof (uint32_t) * (items.size () + 1)));
+  QG_TRY (qg_reserve (ctx, dPR, sizeof (int2) * (run_total + 1)));
+  QG_TRY (qg_reserve (ctx, dPI, sizeof (uint2) * (n_pairs + 1)));
+  QG_TRY (qg_reserve (ctx, dPC, sizeof (unsigned long long) * (n_pairs + 1)));
+  QG_TRY (qg_reserve (ctx, dFL, 64));
+  QG_CUDA (ctx, cudaMemsetAsync (dFL.p, 0, 64, ctx->stream));
+
+  if (!items.empty ()) {
+    QG_TRY (qg_ensure_codes (ctx, x_set, k));
+    QG_TRY (qg_ensure_codes (ctx, QG_READS, k));
+    const uint32_t nk = 1u << (2 * k);
+    uint32_t need = std::max<uint32_t> (nk, QG_SEED_STEP + ymax + 1), ring = 1;
+    while (ring < need) ring <<= 1;
+    const size_t smem = (size_t) ring * 4 + (size_t) ((nk + 2) & ~1u) * 2 + (size_t) ((ymax + 1) & ~1u) * 2 + (QG_SEED_STEP / 32 + 2) * 4;
+    if (smem > ctx->smem_optin)
+      QG_FAIL (ctx, QG_ERR_UNSUPPORTED, "reads of up to %u bases need %zu B of shared memory per seeding CTA (limit %zu)", ymax, smem, ctx->smem_optin);
+    QG_CUDA (ctx, cudaFuncSetAttribute (qg_seed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    {
+      qg_timer tm (ctx, &ctx->stats.ms_seed);
+      QG_LAUNCH (qg_seed_kernel, (unsigned) items.size (), QG_SEED_THREADS, smem, ctx->stream,
+                 dIT.as<qg_seed_item> (), dPD.as<qg_pair_desc> (), ctx->seqs[x_set].d_codes.as<uint16_t> (), ctx->seqs[QG_READS].d_codes.as<uint16_t> (),
+                 k, cfg->kmer_threshold, (int) ((unsigned) cfg->band_size / 2), ring, ymax, run_cap,
+                 dIR.as<int2> (), dIN.as<uint32_t> (), (unsigned long long*) ((char*) dFL.p + 8), (uint32_t*) dFL.p);
+      QG_TRY (qg_check_launch (ctx, "qg_seed_kernel"));
+    }
+  }
+  {
+    qg_timer tm (ctx, &ctx->stats.ms_envelope);
+    QG_LAUNCH (qg_envelope_finalize_kernel, (unsigned) ((n_pairs + 127) / 128), 128, 0, ctx->stream,
+               dPD.as<qg_pair_desc> (), (uint32_t) n_pairs, dIR.as<int2> (), dIN.as<uint32_t> (), run_cap,
+               dPR.as<int2> (), dPI.as<uint2> (), dPC.as<unsigned long long> ());
+    QG_TRY (qg_check_launch (ctx, "qg_envelope_finalize_kernel"));
+  }
+  // small read-back: flags, per-pair run counts, runs
+  uint64_t flags[2] = {0, 0};
+  std::vector<uint2> info (n_pairs);
+  std::vector<unsigned long long> cu (n_pairs);
+  std::vector<int2> pr (run_total + 1);
+  {
+    qg_timer tm (ctx, &ctx->stats.ms_d2h);
+    QG_TRY (qg_download (ctx, flags, dFL.p, 16));
+    QG_TRY (qg_download (ctx, info.data (), dPI.p, sizeof (uint2) * n_pairs));
+    QG_TRY (qg_download (ctx, cu.data (), dPC.p, sizeof (unsigned long long) * n_pairs));
+    QG_TRY (qg_download (ctx, pr.data (), dPR.p, sizeof (int2) * run_total));
+  }
+  if ((uint32_t) flags[0])
+    QG_FAIL (ctx, QG_ERR_UNSUPPORTED, "an envelope has more than %u disjoint runs inside one %d-diagonal chunk; raise QG_RUN_CAP", run_cap, QG_SEED_CHUNK);
+  ctx->stats.kmer_hits += flags[1];
+  out.run_begin.resize (n_pairs + 1);
+  out.runs.clear ();
+  out.cu.assign (cu.begin (), cu.end ());
+  out.ndiag.resize (n_pairs);
+  for (size_t p = 0; p < n_pairs; ++p) {
+    out.run_begin[p] = (uint32_t) out.runs.size ();
+    for (uint32_t r = 0; r < info[p].x; ++r) out.runs.push_back (pr[pd[p].run_out + r]);
+    out.ndiag[p] = info[p].y;
+  }
+  out.run_begin[n_pairs] = (uint32_t) out.runs.size ();
+  ctx->stats.n_pairs += n_pairs;
+  return QG_OK;
+}
+
+extern "C" int qg_envelopes (qg_ctx* ctx, const qg_dpconfig* cfg, uint64_t cell_size, int x_set,
+                             size_t n_pairs, const uint32_t* xi, const uint32_t* yi,
+                             int32_t** diags_out, uint64_t* diag_offsets, uint64_t* cell_updates) {
+  if (!ctx || !cfg || !xi || !yi || !diags_out || !diag_offsets) return QG_ERR_INVALID;
+  if (x_set != QG_REFS && x_set != QG_READS) QG_FAIL (ctx, QG_ERR_INVALID, "x_set must be QG_REFS or QG_READS");
+  qg_env_result er;
+  QG_TRY (qg_envelope_stage (ctx, cfg, cell_size, x_set, n_pairs, xi, yi, er));
+  uint64_t total = 0;
+  for (size_t p = 0; p < n_pairs; ++p) { diag_offsets[p] = total; total += er.ndiag[p]; }
+  diag_offsets[n_pairs] = total;
+  int32_t* d = (int32_t*) malloc (sizeof (int32_t) * (total + 1));
+  if (!d) QG_FAIL (ctx, QG_ERR_INVALID, "out of host memory");
+  uint64_t n = 0;
+  for (size_t p = 0; p < n_pairs; ++p)
+    for (uint32_t r = er.run_begin[p]; r < er.run_begin[p + 1]; ++r)
+      for (int v = er.runs[r].x; v <= er.runs[r].y; ++v) d[n++] = v;
+  *diags_out = d;
+  if (cell_updates) for (size_t p = 0; p < n_pairs; ++p) cell_updates[p] = er.cu[p];
+  return QG_OK;
+}
+
+// ---- DP staging shared by Viterbi / Forward / Backward ----------------------------------------------------------
+struct qg_dp_plan {
+  std::vector<qg_segment> segs;      // grouped by launch class, pairs ascending inside a class? no: see seg_of_pair
+  std::vector<qg_pair_dp> pairs;     // per pair: its segments are contiguous in `segs`
+  struct launch { int R; int nw; uint32_t begin, count; };
+  std::vector<launch> launches;      // each covers segs_sorted[begin, begin+count)
+  std::vector<uint32_t> order;       // launch order -> index into segs
+  std::vector<qg_segment> segs_sorted;
+  uint64_t trace_words = 0, store_doubles = 0, aux_slots = 0, rp_rows = 0;
+  std::vector<qg_rp_job> rp_jobs;
+};
+
+static int qg_pick_R (uint32_t width, int* R, int* nw) {
+  if (width <= 256) { int r = (int) ((width + 31) / 32); if (r < 2) r = 2; *R = r; *nw = 1; return QG_OK; }
+  *R = 8; *nw = (int) ((width + 255) / 256);
+  return (*nw <= QG_MAX_NW) ? QG_OK : QG_ERR_UNSUPPORTED;
+}
+
+// pairs [p0, p1) of the call; trace / store sizing according to `mode` (0 Viterbi, 1 Forward, 2 Forward+store)
+static int qg_build_plan (qg_ctx* ctx, const qg_env_result& er, size_t p0, size_t p1, const uint32_t* xi, const uint32_t* yi,
+                          int x_set, int mode, qg_dp_plan& plan) {
+  const qg_seqset& X = ctx->seqs[x_set];
+  const qg_seqset& Y = ctx->seqs[QG_READS];
+  plan = qg_dp_plan ();
+  std::map<uint32_t, uint64_t> rp_of_read;
+  for (size_t p = p0; p < p1; ++p) {
+    qg_pair_dp pp;
+    pp.seg_begin = (uint32_t) plan.segs.size ();
+    pp.xlen = X.len (xi[p]); pp.ylen = Y.len (yi[p]);
+    auto it = rp_of_read.find (yi[p]);
+    if (it == rp_of_read.end ()) {
+      qg_rp_job jb; jb.yseq = yi[p]; jb.ylen = pp.ylen; jb.yoff = Y.off[yi[p]]; jb.rp_off = plan.rp_rows;
+      plan.rp_jobs.push_back (jb);
+      it = rp_of_read.insert (std::make_pair (yi[p], plan.rp_rows)).first;
+      plan.rp_rows += (uint64_t) pp.ylen + 2;
+    }
+    int dmin = 0, dmax = 0; bool first = true;
+    for (uint32_t r = er.run_begin[p]; r < er.run_begin[p + 1]; ++r) {
+      qg_segment sg;
+      memset (&sg, 0, sizeof (sg));
+      sg.pair = (uint32_t) (p - p0);
+      sg.dlo = er.runs[r].x; sg.width = (uint32_t) (er.runs[r].y - er.runs[r].x + 1);
+      sg.xlen = pp.xlen; sg.ylen = pp.ylen; sg.xseq = xi[p]; sg.yseq = yi[p];
+      int R, nw;
+      if (qg_pick_R (sg.width, &R, &nw) != QG_OK)
+        QG_FAIL (ctx, QG_ERR_UNSUPPORTED, "pair %zu: a run of %u consecutive diagonals exceeds the %d this build fills with one CTA", p, sg.width, 256 * QG_MAX_NW);
+      sg.R = (uint32_t) R; sg.nwarps = (uint32_t) nw;
+      sg.rp_off = it->second;
+      const uint64_t lanes = 32ull * nw;
+      if (mode == 0) { sg.trace_off = plan.trace_words; plan.trace_words += ((uint64_t) pp.ylen + lanes + 1) * lanes; }
+      if (mode == 2) { sg.store_off = plan.store_doubles; plan.store_doubles += ((uint64_t) pp.ylen + 1) * 3 * lanes * R; }
+      if (mode == 0) sg.aux_off = plan.segs.size ();           // Viterbi: index of the segment in pair order
+      else { sg.aux_off = plan.aux_slots; plan.aux_slots += lanes * R; }
+      plan.segs.push_back (sg);
+      if (first) { dmin = er.runs[r].x; dmax = er.runs[r].y; first = false; } else { dmin = std::min (dmin, er.runs[r].x); dmax = std::max (dmax, er.runs[r].y); }
+    }
+    pp.seg_end = (uint32_t) plan.segs.size ();
+    const uint64_t xspan = std::min<uint64_t> (pp.xlen, (uint64_t) pp.ylen + (uint64_t) (dmax - dmin) + 1);
+    pp.path_cap = (uint32_t) (pp.ylen + xspan + 1);
+    pp.path_off = 0; pp.want_path = 0;
+    plan.pairs.push_back (pp);
+  }
+  // launch classes: (nw, R)
+  std::map<std::pair<int,int>, std::vector<uint32_t> > cls;
+  for (uint32_t s = 0; s < plan.segs.size (); ++s) cls[std::make_pair ((int) plan.segs[s].nwarps, (int) plan.segs[s].R)].push_back (s);
+  for (auto& kv : cls) {
+    qg_dp_plan::launch L; L.nw = kv.first.first; L.R = kv.first.second; L.begin = (uint32_t) plan.order.size (); L.count = (uint32_t) kv.second.size ();
+    for (uint32_t s : kv.second) plan.order.push_back (s);
+    plan.launches.push_back (L);
+  }
+  return QG_OK;
+}
+
+template<int MODE>
+static int qg_launch_fill (qg_ctx* ctx, const qg_dp_plan& plan, qg_fill_args a, const qg_segment* d_segs_launch_order) {
+  for (const auto& L : plan.launches) {
+    a.segs = d_segs_launch_order + L.begin;
+    const bool multi = L.nw > 1;
+    const unsigned block = 32u * L.nw;
+#define QG_CASE(RR) case RR: \
+      if (multi) { auto kfn = qg_fill_kernel<8, MODE, true>; QG_LAUNCH (kfn, L.count, block, 0, ctx->stream, a); } \
+      else { auto kfn = qg_fill_kernel<RR, MODE, false>; QG_LAUNCH (kfn, L.count, block, 0, ctx->stream, a); } break;
+    switch (L.R) {
+      QG_CASE (2) QG_CASE (3) QG_CASE (4) QG_CASE (5) QG_CASE (6) QG_CASE (7) QG_CASE (8)
+      default: QG_FAIL (ctx, QG_ERR_INVALID, "internal: unsupported R=%d", L.R);
+    }
+#undef QG_CASE
+    QG_TRY (qg_check_launch (ctx, "qg_fill_kernel"));
+  }
+  return QG_OK;
+}
+
+static int qg_stage_rowparams (qg_ctx* ctx, const qg_dp_plan& plan) {
+  const qg_seqset& Y = ctx->seqs[QG_READS];
+  const qg_model_dev& m = ctx->model;
+  QG_TRY (qg_upload (ctx, ctx->scratch[SC_RPJOBS], plan.rp_jobs.data (), sizeof (qg_rp_job) * plan.rp_jobs.size ()));
+  QG_TRY (qg_reserve (ctx, ctx->scratch[SC_RP], sizeof (qg_rowp) * (plan.rp_rows + 1)));
+  if (!plan.rp_jobs.empty ()) {
+    QG_LAUNCH (qg_rowparams_kernel, (unsigned) plan.rp_jobs.size (), 256, 0, ctx->stream,
+               ctx->scratch[SC_RPJOBS].as<qg_rp_job> (), Y.d_tok.as<uint8_t> (), Y.has_qual ? Y.d_qual.as<uint8_t> () : (const uint8_t*) nullptr,
+               m.d_match.as<double> (), m.d_insert.as<double> (), m.d_gap.as<double> (), m.match_k, m.gap_k, ctx->scratch[SC_RP].as<qg_rowp> ());
+    QG_TRY (qg_check_launch (ctx, "qg_rowparams_kernel"));
+  }
+  return QG_OK;
+}
+
+static qg_fill_args qg_base_args (qg_ctx* ctx, const qg_dpconfig* cfg, int x_set) {
+  qg_fill_args a;
+  memset (&a, 0, sizeof (a));
+  a.xpacked = ctx->seqs[x_set].d_packed.as<uint64_t> ();
+  a.xpoff = ctx->seqs[x_set].d_poff.as<uint64_t> ();
+  a.rp = ctx->scratch[SC_RP].as<qg_rowp> ();
+  a.lse = ctx->d_lse.as<double> ();
+  a.i2i = ctx->model.i2i; a.i2m = ctx->model.i2m; a.d2d = ctx->model.d2d; a.d2m = ctx->model.d2m;
+  a.local = cfg->local;
+  return a;
+}
+
+static int qg_check_ready (qg_ctx* ctx, const qg_dpconfig* cfg) {
+  if (!ctx->model.set) QG_FAIL (ctx, QG_ERR_STATE, "no align model: call qg_set_align_model first");
+  if (!ctx->seqs[QG_REFS].n || !ctx->seqs[QG_READS].n) QG_FAIL (ctx, QG_ERR_STATE, "sequence sets not uploaded: call qg_set_seqs for QG_REFS and QG_READS");
+  if (cfg->band_size < 0) QG_FAIL (ctx, QG_ERR_INVALID, "negative band size");
+  return QG_OK;
+}
+
+static uint64_t qg_plan_cells (const qg_env_result& er, size_t p0, size_t p1) {
+  uint64_t cu = 0;
+  for (size_t p = p0; p < p1; ++p) cu += er.cu[p];
+  return cu;
+}
+
+// ---- Viterbi -------------------------------------------------------------------------------------------------------
+extern "C" int qg_viterbi (qg_ctx* ctx, const qg_dpconfig* cfg, size_t n_pairs, const uint32_t* xi, const uint32_t* yi,
+                           const uint8_t* want_path, double* score, uint32_t* x_start, uint32_t* x_end,
+                           uint8_t** path_out, uint64_t* path_offsets) {
+  if (!ctx || !cfg || !xi || !yi || !score) return QG_ERR_INVALID;
+  QG_TRY (qg_check_ready (ctx, cfg));
+  const bool paths = path_out && path_offsets && x_start && x_end;
+  if (path_out) *path_out = nullptr;
+  qg_env_result er;
+  QG_TRY (qg_envelope_stage (ctx, cfg, 24, QG_REFS, n_pairs, xi, yi, er));
+
+  // sub-batches bounded by pointer memory
+  size_t freeb = 0, totb = 0;
+  QG_CUDA (ctx, cudaMemGetInfo (&freeb, &totb));
+  const uint64_t budget = (uint64_t) qg_env_size ("QG_TRACE_BUDGET_MB", std::min<size_t> (freeb / 2, (size_t) 32 << 30) >> 20) << 20;
+  std::vector<uint8_t> all_paths;
+  std::vector<uint64_t> offs (n_pairs + 1, 0);
+  uint64_t path_total = 0;
+  size_t p0 = 0;
+  while (p0 < n_pairs) {
+    // grow the batch while the trace fits
+    size_t p1 = p0; uint64_t words = 0;
+    while (p1 < n_pairs) {
+      uint64_t w = 0;
+      for (uint32_t r = er.run_begin[p1]; r < er.run_begin[p1 + 1]; ++r) {
+        int R, nw; const uint32_t width = (uint32_t) (er.runs[r].y - er.runs[r].x + 1);
+        if (qg_pick_R (width, &R, &nw) != QG_OK) QG_FAIL (ctx, QG_ERR_UNSUPPORTED, "pair %zu: a run of %u consecutive diagonals exceeds the %d this build fills with one CTA", p1, width, 256 * QG_MAX_NW);
+        w += ((uint64_t) ctx->seqs[QG_READS].len (yi[p1]) + 32ull * nw + 1) * 32ull * nw;
+      }
+      if (p1 > p0 && (words + w) * 4 > budget) break;
+      words += w; ++p1;
+    }
+    qg_dp_plan plan;
+    QG_TRY (qg_build_plan (ctx, er, p0, p1, xi, yi, QG_REFS, 0, plan));
+    const size_t np = p1 - p0;
+    uint64_t scratch_bytes = 0;
+    for (size_t p = 0; p < np; ++p) {
+      plan.pairs[p].want_path = paths && (!want_path || want_path[p0 + p]) ? 1 : 0;
+      plan.pairs[p].path_off = scratch_bytes;
+      if (plan.pairs[p].want_path) scratch_bytes += plan.pairs[p].path_cap;
+    }
+    for (uint32_t s : plan.order) plan.segs_sorted.push_back (plan.segs[s]);
+    // seg_end is indexed by launch order (blockIdx of the class launch + class begin) -> remap per pair below
+    {
+      qg_timer tm (ctx, &ctx->stats.ms_prep);
+      QG_TRY (qg_stage_rowparams (ctx, plan));
+      QG_TRY (qg_upload (ctx, ctx->scratch[SC_SEGS], plan.segs_sorted.data (), sizeof (qg_segment) * plan.segs_sorted.size ()));
+      QG_TRY (qg_reserve (ctx, ctx->scratch[SC_TRACE], sizeof (uint32_t) * (plan.trace_words + 1)));
+      QG_TRY (qg_reserve (ctx, ctx->scratch[SC_ENDVALS], sizeof (double) * 2 * (plan.segs.size () + 1)));
+    }
+    ctx->stats.trace_bytes += plan.trace_words * 4;
+    ctx->stats.n_segments += plan.segs.size ();
+    ctx->stats.cell_updates += qg_plan_cells (er, p0, p1);
+    {
+      qg_timer tm (ctx, &ctx->stats.ms_viterbi);
+      qg_fill_args a = qg_base_args (ctx, cfg, QG_REFS);
+      a.trace = ctx->scratch[SC_TRACE].as<uint32_t> ();
+      a.endvals = ctx->scratch[SC_ENDVALS].as<double> ();       // {score, i} per segment, indexed by seg.aux_off (pair order)
+      QG_TRY (qg_launch_fill<0> (ctx, plan, a, ctx->scratch[SC_SEGS].as<qg_segment> ()));
+    }
+    {
+      qg_timer tm (ctx, &ctx->stats.ms_traceback);
+      QG_TRY (qg_upload (ctx, ctx->scratch[SC_MISC0], plan.segs.data (), sizeof (qg_segment) * plan.segs.size ()));
+      QG_TRY (qg_upload (ctx, ctx->scratch[SC_PAIRDP], plan.pairs.data (), sizeof (qg_pair_dp) * np));
+      QG_TRY (qg_reserve (ctx, ctx->scratch[SC_OUT0], sizeof (double) * (np + 1)));
+      QG_TRY (qg_reserve (ctx, ctx->scratch[SC_OUT1], sizeof (uint32_t) * (np + 1)));
+      QG_TRY (qg_reserve (ctx, ctx->scratch[SC_OUT2], sizeof (uint32_t) * (np + 1)));
+      QG_TRY (qg_reserve (ctx, ctx->scratch[SC_OUT3], sizeof (uint32_t) * (np + 1)));
+      QG_TRY (qg_reserve (ctx, ctx->scratch[SC_PATHSCR], scratch_bytes + 16));
+      QG_CUDA (ctx, cudaMemsetAsync (ctx->scratch[SC_FLAGS].p, 0, 64, ctx->stream));
+      QG_LAUNCH (qg_traceback_kernel, (unsigned) ((np + 63) / 64), 64, 0, ctx->stream,
+                 ctx->scratch[SC_PAIRDP].as<qg_pair_dp> (), (uint32_t) np, ctx->scratch[SC_MISC0].as<qg_segment> (),
+                 ctx->scratch[SC_ENDVALS].as<double> (), ctx->scratch[SC_TRACE].as<uint32_t> (),
+                 ctx->scratch[SC_OUT0].as<double> (), ctx->scratch[SC_OUT1].as<uint32_t> (), ctx->scratch[SC_OUT2].as<uint32_t> (),
+                 ctx->scratch[SC_PATHSCR].as<uint8_t> (), ctx->scratch[SC_OUT3].as<uint32_t> (), (uint32_t*) ctx->scratch[SC_FLAGS].p);
+      QG_TRY (qg_check_launch (ctx, "qg_traceback_kernel"));
+    }
+    std::vector<uint32_t> plen (np), xs (np), xe (np);
+    uint32_t flag = 0;
+    {
+      qg_timer tm (ctx, &ctx->stats.ms_d2h);
+      QG_TRY (qg_download (ctx, score + p0, ctx->scratch[SC_OUT0].p, sizeof (double) * np));
+      QG_TRY (qg_download (ctx, xs.data (), ctx->scratch[SC_OUT1].p, sizeof (uint32_t) * np));
+      QG_TRY (qg_download (ctx, xe.data (), ctx->scratch[SC_OUT2].p, sizeof (uint32_t) * np));
+      QG_TRY (qg_download (ctx, plen.data (), ctx->scratch[SC_OUT3].p, sizeof (uint32_t) * np));
+      QG_TRY (qg_download (ctx, &flag, ctx->scratch[SC_FLAGS].p, sizeof (uint32_t)));
+    }
+    if (flag) QG_FAIL (ctx, QG_ERR_CUDA, "internal: traceback left the envelope (code %u)", flag);
+    if (x_start) for (size_t p = 0; p < np; ++p) { x_start[p0 + p] = xs[p]; x_end[p0 + p] = xe[p]; }
+    if (paths) {
+      std::vector<uint64_t> goff (np + 1, 0);
+      for (size_t p = 0; p < np; ++p) goff[p + 1] = goff[p] + plen[p];
+      for (size_t p = 0; p < np; ++p) offs[p0 + p] = path_total + goff[p];
+      if (goff[np]) {
+        qg_timer tm (ctx, &ctx->stats.ms_d2h);
+        QG_TRY (qg_upload (ctx, ctx->scratch[SC_MISC1], goff.data (), sizeof (uint64_t) * (np + 1)));
+        QG_TRY (qg_reserve (ctx, ctx->scratch[SC_PATHOUT], goff[np] + 16));
+        QG_LAUNCH (qg_path_gather_kernel, (unsigned) np, 128, 0, ctx->stream,
+                   ctx->scratch[SC_PAIRDP].as<qg_pair_dp> (), (uint32_t) np, ctx->scratch[SC_PATHSCR].as<uint8_t> (),
+                   ctx->scratch[SC_OUT3].as<uint32_t> (), ctx->scratch[SC_MISC1].as<uint64_t> (), ctx->scratch[SC_PATHOUT].as<uint8_t> ());
+        QG_TRY (qg_check_launch (ctx, "qg_path_gather_kernel"));
+        all_paths.resize (path_total + goff[np]);
+        QG_TRY (qg_download (ctx, all_paths.data () + path_total, ctx->scratch[SC_PATHOUT].p, goff[np]));
+      }
+      path_total += goff[np];
+    }
+    p0 = p1;
+  }
+  if (paths) {
+    offs[n_pairs] = path_total;
+    memcpy (path_offsets, offs.data (), sizeof (uint64_t) * (n_pairs + 1));
+    uint8_t* buf = (uint8_t*) malloc (path_total + 1);
+    if (!buf) QG_FAIL (ctx, QG_ERR_INVALID, "out of host memory");
+    if (path_total) memcpy (buf, all_paths.data (), path_total);
+    *path_out = buf;
+  }
+  return QG_OK;
+}
+
+// ---- Forward --------------------------------------------------------------------------------------------------------
+extern "C" int qg_forward (qg_ctx* ctx, const qg_dpconfig* cfg, size_t n_pairs, const uint32_t* xi, const uint32_t* yi, double* loglike) {
+  if (!ctx || !cfg || !xi || !yi || !loglike) return QG_ERR_INVALID;
+  QG_TRY (qg_check_ready (ctx, cfg));
+  qg_env_result er;
+  QG_TRY (qg_envelope_stage (ctx, cfg, 48, QG_REFS, n_pairs, xi, yi, er));
+  qg_dp_plan plan;
+  QG_TRY (qg_build_plan (ctx, er, 0, n_pairs, xi, yi, QG_REFS, 1, plan));
+  // Forward folds end values per pair in pair order: keep segs in pair order, launch classes through an index
+  for (uint32_t s : plan.order) plan.segs_sorted.push_back (plan.segs[s]);
+  {
+    qg_timer tm (ctx, &ctx->stats.ms_prep);
+    QG_TRY (qg_stage_rowparams (ctx, plan));
+    QG_TRY (qg_upload (ctx, ctx->scratch[SC_SEGS], plan.segs_sorted.data (), sizeof (qg_segment) * plan.segs_sorted.size ()));
+    QG_TRY (qg_upload (ctx, ctx->scratch[SC_MISC0], plan.segs.data (), sizeof (qg_segment) * plan.segs.size ()));
+    QG_TRY (qg_reserve (ctx, ctx->scratch[SC_ENDVALS], sizeof (double) * (plan.aux_slots + 1)));
+    QG_TRY (qg_upload (ctx, ctx->scratch[SC_PAIRDP], plan.pairs.data (), sizeof (qg_pair_dp) * n_pairs));
+    QG_TRY (qg_reserve (ctx, ctx->scratch[SC_OUT0], sizeof (double) * (n_pairs + 1)));
+  }
+  ctx->stats.n_segments += plan.segs.size ();
+  ctx->stats.cell_updates += qg_plan_cells (er, 0, n_pairs);
+  {
+    qg_timer tm (ctx, &ctx->stats.ms_forward);
+    qg_fill_args a = qg_base_args (ctx, cfg, QG_REFS);
+    a.endvals = ctx->scratch[SC_ENDVALS].as<double> ();
+    QG_TRY (qg_launch_fill<1> (ctx, plan, a, ctx->scratch[SC_SEGS].as<qg_segment> ()));
+    QG_LAUNCH (qg_forward_finalize_kernel, (unsigned) ((n_pairs + 63) / 64), 64, 0, ctx->stream,
+               ctx->scratch[SC_PAIRDP].as<qg_pair_dp> (), (uint32_t) n_pairs, ctx->scratch[SC_MISC0].as<qg_segment> (),
+               ctx->scratch[SC_ENDVALS].as<double> (), ctx->d_lse.as<double> (), ctx->scratch[SC_OUT0].as<double> ());
+    QG_TRY (qg_check_launch (ctx, "qg_forward_finalize_kernel"));
+  }
+  {
+    qg_timer tm (ctx, &ctx->stats.ms_d2h);
+    QG_TRY (qg_download (ctx, loglike, ctx->scratch[SC_OUT0].p, sizeof (double) * n_pairs));
+  }
+  return QG_OK;
+}
