@@ -96,7 +96,9 @@ struct qg_segment {
   uint64_t trace_off;                // word offset of this segment's pointer block
   uint64_t store_off;                // double offset of this segment's stored Forward matrix
   uint64_t rp_off;                   // row offset of the read's row-parameter block
-  uint64_t aux_off;                  // offset into the per-segment end-value / store area
+  uint64_t aux_off;                  // offset into the per-segment end-value area (Viterbi: pair-order segment index)
+  uint64_t acc_off;                  // Backward: row offset of this segment's per-row count sums
+  uint64_t seg_id;                   // pair-order index of the segment
 };
 
 struct qg_ctx {

@@ -4,6 +4,7 @@
 #include "qg_common.cuh"
 #include "qg_seed.cuh"
 #include "qg_dp.cuh"
+#include "qg_backward.cuh"
 #include <map>
 #include <numeric>
 
@@ -247,15 +248,15 @@ struct qg_env_result {
   std::vector<uint32_t> ndiag;       // [n_pairs]
 };
 
-static int qg_envelope_stage (qg_ctx* ctx, const qg_dpconfig* cfg, uint64_t cell_size, int x_set,
-                              size_t n_pairs, const uint32_t* xi, const uint32_t* yi, qg_env_result& out) {
+static int qg_envelope_stage_cap (qg_ctx* ctx, const qg_dpconfig* cfg, uint64_t cell_size, int x_set,
+                                  size_t n_pairs, const uint32_t* xi, const uint32_t* yi, qg_env_result& out, uint32_t run_cap, bool* overflow) {
   (void) cell_size;
+  *overflow = false;
   const qg_seqset& X = ctx->seqs[x_set];
   const qg_seqset& Y = ctx->seqs[QG_READS];
   const int k = cfg->kmer_len;
   std::vector<qg_pair_desc> pd (n_pairs);
   std::vector<qg_seed_item> items;
-  const uint32_t run_cap = (uint32_t) qg_env_size ("QG_RUN_CAP", 64);
   bool any_sparse = false;
   uint32_t ymax = 0;
   uint64_t run_total = 0;
@@ -343,8 +344,7 @@ static int qg_envelope_stage (qg_ctx* ctx, const qg_dpconfig* cfg, uint64_t cell
     QG_TRY (qg_download (ctx, cu.data (), dPC.p, sizeof (unsigned long long) * n_pairs));
     QG_TRY (qg_download (ctx, pr.data (), dPR.p, sizeof (int2) * run_total));
   }
-  if ((uint32_t) flags[0])
-    QG_FAIL (ctx, QG_ERR_UNSUPPORTED, "an envelope has more than %u disjoint runs inside one %d-diagonal chunk; raise QG_RUN_CAP", run_cap, QG_SEED_CHUNK);
+  if ((uint32_t) flags[0]) { *overflow = true; return QG_OK; }
   ctx->stats.kmer_hits += flags[1];
   out.run_begin.resize (n_pairs + 1);
   out.runs.clear ();
@@ -358,6 +358,22 @@ static int qg_envelope_stage (qg_ctx* ctx, const qg_dpconfig* cfg, uint64_t cell
   out.run_begin[n_pairs] = (uint32_t) out.runs.size ();
   ctx->stats.n_pairs += n_pairs;
   return QG_OK;
+}
+
+// run buffers are sized for the common case (a handful of runs per 192k-diagonal chunk) and grown on demand up
+// to the most runs a chunk can hold, chunk / (band + 2) + 2
+static int qg_envelope_stage (qg_ctx* ctx, const qg_dpconfig* cfg, uint64_t cell_size, int x_set,
+                              size_t n_pairs, const uint32_t* xi, const uint32_t* yi, qg_env_result& out) {
+  const uint32_t half = (uint32_t) cfg->band_size / 2;
+  const uint32_t cap_max = QG_SEED_CHUNK / (2 * half + 2) + 3;
+  uint32_t cap = (uint32_t) qg_env_size ("QG_RUN_CAP", 64);
+  while (true) {
+    bool overflow = false;
+    QG_TRY (qg_envelope_stage_cap (ctx, cfg, cell_size, x_set, n_pairs, xi, yi, out, cap, &overflow));
+    if (!overflow) return QG_OK;
+    if (cap >= cap_max) QG_FAIL (ctx, QG_ERR_CUDA, "internal: run buffer overflow at the theoretical maximum of %u runs per chunk", cap);
+    cap = std::min<uint64_t> ((uint64_t) cap * 16, cap_max);
+  }
 }
 
 extern "C" int qg_envelopes (qg_ctx* ctx, const qg_dpconfig* cfg, uint64_t cell_size, int x_set,
@@ -389,7 +405,7 @@ struct qg_dp_plan {
   std::vector<launch> launches;      // each covers segs_sorted[begin, begin+count)
   std::vector<uint32_t> order;       // launch order -> index into segs
   std::vector<qg_segment> segs_sorted;
-  uint64_t trace_words = 0, store_doubles = 0, aux_slots = 0, rp_rows = 0;
+  uint64_t trace_words = 0, store_doubles = 0, aux_slots = 0, rp_rows = 0, acc_rows = 0;
   std::vector<qg_rp_job> rp_jobs;
 };
 
@@ -431,7 +447,9 @@ static int qg_build_plan (qg_ctx* ctx, const qg_env_result& er, size_t p0, size_
       sg.rp_off = it->second;
       const uint64_t lanes = 32ull * nw;
       if (mode == 0) { sg.trace_off = plan.trace_words; plan.trace_words += ((uint64_t) pp.ylen + lanes + 1) * lanes; }
-      if (mode == 2) { sg.store_off = plan.store_doubles; plan.store_doubles += ((uint64_t) pp.ylen + 1) * 3 * lanes * R; }
+      if (mode == 2) { sg.store_off = plan.store_doubles; plan.store_doubles += ((uint64_t) pp.ylen + 1) * 3 * lanes * R;
+                       sg.acc_off = plan.acc_rows; plan.acc_rows += (uint64_t) pp.ylen + 2; }
+      sg.seg_id = plan.segs.size ();
       if (mode == 0) sg.aux_off = plan.segs.size ();           // Viterbi: index of the segment in pair order
       else { sg.aux_off = plan.aux_slots; plan.aux_slots += lanes * R; }
       plan.segs.push_back (sg);
@@ -666,5 +684,125 @@ extern "C" int qg_forward (qg_ctx* ctx, const qg_dpconfig* cfg, size_t n_pairs, 
     qg_timer tm (ctx, &ctx->stats.ms_d2h);
     QG_TRY (qg_download (ctx, loglike, ctx->scratch[SC_OUT0].p, sizeof (double) * n_pairs));
   }
+  return QG_OK;
+}
+
+// ---- Backward + counts ----------------------------------------------------------------------------------------------
+template<int DUMMY>
+static int qg_launch_backward (qg_ctx* ctx, const qg_dp_plan& plan, qg_fill_args a, const qg_segment* d_segs_launch_order) {
+  for (const auto& L : plan.launches) {
+    a.segs = d_segs_launch_order + L.begin;
+    const bool multi = L.nw > 1;
+    const unsigned block = 32u * L.nw;
+#define QG_CASE(RR) case RR: \
+      if (multi) { auto kfn = qg_backward_kernel<8, true>; QG_LAUNCH (kfn, L.count, block, 0, ctx->stream, a); } \
+      else { auto kfn = qg_backward_kernel<RR, false>; QG_LAUNCH (kfn, L.count, block, 0, ctx->stream, a); } break;
+    switch (L.R) {
+      QG_CASE (2) QG_CASE (3) QG_CASE (4) QG_CASE (5) QG_CASE (6) QG_CASE (7) QG_CASE (8)
+      default: QG_FAIL (ctx, QG_ERR_INVALID, "internal: unsupported R=%d", L.R);
+    }
+#undef QG_CASE
+    QG_TRY (qg_check_launch (ctx, "qg_backward_kernel"));
+  }
+  return QG_OK;
+}
+
+extern "C" int qg_backward_counts (qg_ctx* ctx, const qg_dpconfig* cfg, size_t n_pairs, const uint32_t* xi, const uint32_t* yi,
+                                   const double* weights, double* fwd_loglike, double* back_loglike,
+                                   double* counts_sum, double* counts_per_pair) {
+  if (!ctx || !cfg || !xi || !yi) return QG_ERR_INVALID;
+  QG_TRY (qg_check_ready (ctx, cfg));
+  const qg_seqset& Y = ctx->seqs[QG_READS];
+  if (!Y.has_qual) QG_FAIL (ctx, QG_ERR_INVALID, "Forward-Backward requires quality scores (qmodel.cpp:1398)");
+  const qg_model_dev& m = ctx->model;
+  const uint64_t nC = qg_counts_size (m.match_k, m.gap_k);
+  qg_env_result er;
+  QG_TRY (qg_envelope_stage (ctx, cfg, 48, QG_REFS, n_pairs, xi, yi, er));
+  size_t freeb = 0, totb = 0;
+  QG_CUDA (ctx, cudaMemGetInfo (&freeb, &totb));
+  const uint64_t budget = (uint64_t) qg_env_size ("QG_STORE_BUDGET_MB", std::min<size_t> (freeb / 2, (size_t) 48 << 30) >> 20) << 20;
+  qg_dbuf& dSum = ctx->scratch[SC_OUT3];
+  QG_TRY (qg_reserve (ctx, dSum, sizeof (double) * (nC + 1)));
+  QG_CUDA (ctx, cudaMemsetAsync (dSum.p, 0, sizeof (double) * nC, ctx->stream));
+  size_t p0 = 0;
+  while (p0 < n_pairs) {
+    size_t p1 = p0; uint64_t bytes = 0;
+    while (p1 < n_pairs) {
+      uint64_t b = nC * 8;
+      for (uint32_t r = er.run_begin[p1]; r < er.run_begin[p1 + 1]; ++r) {
+        int R, nw; const uint32_t width = (uint32_t) (er.runs[r].y - er.runs[r].x + 1);
+        if (qg_pick_R (width, &R, &nw) != QG_OK) QG_FAIL (ctx, QG_ERR_UNSUPPORTED, "pair %zu: a run of %u consecutive diagonals exceeds the %d this build fills with one CTA", p1, width, 256 * QG_MAX_NW);
+        b += ((uint64_t) Y.len (yi[p1]) + 1) * 3 * 32ull * nw * R * 8 + ((uint64_t) Y.len (yi[p1]) + 2) * 64;
+      }
+      if (p1 > p0 && bytes + b > budget) break;
+      bytes += b; ++p1;
+    }
+    const size_t np = p1 - p0;
+    qg_dp_plan plan;
+    QG_TRY (qg_build_plan (ctx, er, p0, p1, xi, yi, QG_REFS, 2, plan));
+    for (uint32_t s : plan.order) plan.segs_sorted.push_back (plan.segs[s]);
+    {
+      qg_timer tm (ctx, &ctx->stats.ms_prep);
+      QG_TRY (qg_stage_rowparams (ctx, plan));
+      QG_TRY (qg_upload (ctx, ctx->scratch[SC_SEGS], plan.segs_sorted.data (), sizeof (qg_segment) * plan.segs_sorted.size ()));
+      QG_TRY (qg_upload (ctx, ctx->scratch[SC_MISC0], plan.segs.data (), sizeof (qg_segment) * plan.segs.size ()));
+      QG_TRY (qg_reserve (ctx, ctx->scratch[SC_ENDVALS], sizeof (double) * (plan.aux_slots + 1)));
+      QG_TRY (qg_upload (ctx, ctx->scratch[SC_PAIRDP], plan.pairs.data (), sizeof (qg_pair_dp) * np));
+      QG_TRY (qg_reserve (ctx, ctx->scratch[SC_OUT0], sizeof (double) * (np + 1)));
+      QG_TRY (qg_reserve (ctx, ctx->scratch[SC_OUT1], sizeof (double) * (np + 1)));
+      QG_TRY (qg_reserve (ctx, ctx->scratch[SC_STORE], sizeof (double) * (plan.store_doubles + 1)));
+      QG_TRY (qg_reserve (ctx, ctx->scratch[SC_ROWACC], sizeof (qg_rowrec) * (plan.acc_rows + 1)));
+      QG_TRY (qg_reserve (ctx, ctx->scratch[SC_MISC1], sizeof (double) * 12 * (plan.segs.size () + 1)));
+      QG_TRY (qg_reserve (ctx, ctx->scratch[SC_PATHSCR], sizeof (double) * nC * np + 16));
+      QG_CUDA (ctx, cudaMemsetAsync (ctx->scratch[SC_MISC1].p, 0, sizeof (double) * 12 * (plan.segs.size () + 1), ctx->stream));
+      QG_CUDA (ctx, cudaMemsetAsync (ctx->scratch[SC_PATHSCR].p, 0, sizeof (double) * nC * np, ctx->stream));
+      QG_CUDA (ctx, cudaMemsetAsync (ctx->scratch[SC_ROWACC].p, 0, sizeof (qg_rowrec) * (plan.acc_rows + 1), ctx->stream));
+    }
+    ctx->stats.n_segments += plan.segs.size ();
+    ctx->stats.cell_updates += 2 * qg_plan_cells (er, p0, p1);
+    ctx->stats.fwd_store_bytes += plan.store_doubles * 8;
+    qg_fill_args a = qg_base_args (ctx, cfg, QG_REFS);
+    a.endvals = ctx->scratch[SC_ENDVALS].as<double> ();
+    a.store = ctx->scratch[SC_STORE].as<double> ();
+    a.rowacc = ctx->scratch[SC_ROWACC].as<double> ();
+    a.pair_z = ctx->scratch[SC_OUT0].as<double> ();
+    a.seg_scal = ctx->scratch[SC_MISC1].as<double> ();
+    {
+      qg_timer tm (ctx, &ctx->stats.ms_forward);
+      QG_TRY (qg_launch_fill<2> (ctx, plan, a, ctx->scratch[SC_SEGS].as<qg_segment> ()));
+      QG_LAUNCH (qg_forward_finalize_kernel, (unsigned) ((np + 63) / 64), 64, 0, ctx->stream,
+                 ctx->scratch[SC_PAIRDP].as<qg_pair_dp> (), (uint32_t) np, ctx->scratch[SC_MISC0].as<qg_segment> (),
+                 ctx->scratch[SC_ENDVALS].as<double> (), ctx->d_lse.as<double> (), ctx->scratch[SC_OUT0].as<double> ());
+      QG_TRY (qg_check_launch (ctx, "qg_forward_finalize_kernel"));
+    }
+    {
+      qg_timer tm (ctx, &ctx->stats.ms_backward);
+      QG_TRY (qg_launch_backward<0> (ctx, plan, a, ctx->scratch[SC_SEGS].as<qg_segment> ()));
+      QG_LAUNCH (qg_backward_finalize_kernel, (unsigned) ((np + 63) / 64), 64, 0, ctx->stream,
+                 ctx->scratch[SC_PAIRDP].as<qg_pair_dp> (), (uint32_t) np, ctx->scratch[SC_MISC0].as<qg_segment> (),
+                 ctx->scratch[SC_ENDVALS].as<double> (), ctx->d_lse.as<double> (), ctx->scratch[SC_OUT1].as<double> ());
+      QG_TRY (qg_check_launch (ctx, "qg_backward_finalize_kernel"));
+      QG_LAUNCH (qg_counts_scatter_kernel, (unsigned) np, 256, 0, ctx->stream,
+                 ctx->scratch[SC_PAIRDP].as<qg_pair_dp> (), ctx->scratch[SC_MISC0].as<qg_segment> (),
+                 Y.d_tok.as<uint8_t> (), Y.d_qual.as<uint8_t> (), Y.d_off.as<uint64_t> (),
+                 (const qg_rowrec*) ctx->scratch[SC_ROWACC].p, ctx->scratch[SC_MISC1].as<double> (),
+                 m.match_k, m.gap_k, nC, ctx->scratch[SC_PATHSCR].as<double> ());
+      QG_TRY (qg_check_launch (ctx, "qg_counts_scatter_kernel"));
+      const double* dW = nullptr;
+      if (weights) { QG_TRY (qg_upload (ctx, ctx->scratch[SC_OUT2], weights + p0, sizeof (double) * np)); dW = ctx->scratch[SC_OUT2].as<double> (); }
+      QG_LAUNCH (qg_counts_reduce_kernel, (unsigned) ((nC + 127) / 128), 128, 0, ctx->stream,
+                 ctx->scratch[SC_PATHSCR].as<double> (), dW, (uint32_t) np, nC, dSum.as<double> ());
+      QG_TRY (qg_check_launch (ctx, "qg_counts_reduce_kernel"));
+    }
+    {
+      qg_timer tm (ctx, &ctx->stats.ms_d2h);
+      if (fwd_loglike) QG_TRY (qg_download (ctx, fwd_loglike + p0, ctx->scratch[SC_OUT0].p, sizeof (double) * np));
+      if (back_loglike) QG_TRY (qg_download (ctx, back_loglike + p0, ctx->scratch[SC_OUT1].p, sizeof (double) * np));
+      if (counts_per_pair) QG_TRY (qg_download (ctx, counts_per_pair + (uint64_t) p0 * nC, ctx->scratch[SC_PATHSCR].p, sizeof (double) * nC * np));
+    }
+    p0 = p1;
+  }
+  if (counts_sum) { qg_timer tm (ctx, &ctx->stats.ms_d2h); QG_TRY (qg_download (ctx, counts_sum, dSum.p, sizeof (double) * nC)); }
+  QG_CUDA (ctx, cudaStreamSynchronize (ctx->stream));
   return QG_OK;
 }

@@ -1,0 +1,98 @@
+"""Shared parity checks: the CUDA library (real device, or the CPU-thread emulation in the not-gpu
+suite) against the oracle on the same seeded inputs."""
+from __future__ import annotations
+
+import numpy as np
+
+from oracle import pyoracle as po
+from quaff_b200 import api
+from quaff_b200.params import QuaffNullParams, QuaffParams, random_params
+from quaff_b200.seqs import FastSeq, add_revcomps
+from quaff_b200.synth import random_ref, sample_reads
+
+DEFAULT_PARAMS_JSON = None
+
+
+def default_params() -> QuaffParams:
+    """The reference's built-in parameters (data/defaultparams.json), committed as a golden fixture."""
+    import os
+    here = os.path.dirname(os.path.abspath(__file__))
+    return QuaffParams.load(os.path.join(here, "golden", "defaultparams.json"))
+
+
+def make_workload(ref_len, n_reads, read_len, seed, both_strands=True, n_refs=1):
+    refs = [random_ref(ref_len, seed + 100 * r, name=f"ref{r}") for r in range(n_refs)]
+    reads = []
+    for r, rf in enumerate(refs):
+        rd, _, _ = sample_reads(rf, n_reads, read_len, seed + 1 + 100 * r, name_prefix=f"r{r}_")
+        reads += rd
+    x = add_revcomps(refs) if both_strands else refs
+    return x, reads
+
+
+def all_pairs(nx, ny):
+    xi = np.tile(np.arange(nx, dtype=np.uint32), ny)
+    yi = np.repeat(np.arange(ny, dtype=np.uint32), nx)
+    return xi, yi
+
+
+def oracle_cfg(cfg: api.DPConfig) -> po.CConfig:
+    return po.make_config(cfg.sparse, cfg.kmer_len, cfg.kmer_threshold, cfg.band_size, cfg.local, cfg.max_size)
+
+
+def seqbufs(x, reads, use_quals=True):
+    xs = [po.SeqBuf(s.tokens(), None) for s in x]
+    ys = [po.SeqBuf(s.tokens(), s.qual_scores() if use_quals else None) for s in reads]
+    return xs, ys
+
+
+def check_envelopes(G, O, x, reads, cfg, xi, yi, cell_size=24):
+    xs, ys = seqbufs(x, reads)
+    env, cu = G.envelopes(cfg, xi, yi, cell_size=cell_size)
+    oc = oracle_cfg(cfg)
+    for p, (a, b) in enumerate(zip(xi, yi)):
+        d, c = O.envelope(xs[a], ys[b], oc, cell_size)
+        assert np.array_equal(d, env[p]), f"pair {p}: envelope differs ({len(d)} vs {len(env[p])} diagonals)"
+        assert c == cu[p], f"pair {p}: cell updates {c} vs {cu[p]}"
+    return cu
+
+
+def check_viterbi(G, O, x, reads, s_or, cfg, xi, yi, use_quals=True):
+    """bit-exact: score, interval and the whole state path"""
+    xs, ys = seqbufs(x, reads, use_quals)
+    v = G.viterbi(cfg, xi, yi)
+    oc = oracle_cfg(cfg)
+    for p, (a, b) in enumerate(zip(xi, yi)):
+        o = O.viterbi(xs[a], ys[b], s_or, oc)
+        assert o["result"] == v["score"][p] or (np.isinf(o["result"]) and np.isinf(v["score"][p])), (p, o["result"], v["score"][p])
+        assert o["x_start"] == v["x_start"][p] and o["x_end"] == v["x_end"][p], (p, o["x_start"], o["x_end"], v["x_start"][p], v["x_end"][p])
+        assert np.array_equal(o["path"], v["paths"][p]), f"pair {p}: path differs"
+    return v
+
+
+def check_forward(G, O, x, reads, s_or, cfg, xi, yi, use_quals=True):
+    """bit-exact (same table log-sum-exp, same fold order); the stated tolerance is 1e-3 nats per read"""
+    xs, ys = seqbufs(x, reads, use_quals)
+    f = G.forward(cfg, xi, yi)
+    oc = oracle_cfg(cfg)
+    for p, (a, b) in enumerate(zip(xi, yi)):
+        o = O.forward(xs[a], ys[b], s_or, oc)
+        assert o["result"] == f[p] or (np.isinf(o["result"]) and np.isinf(f[p])), (p, o["result"], f[p])
+    return f
+
+
+def check_backward(G, O, x, reads, s_or, cfg, xi, yi, rel=1e-9):
+    """counts within 1e-4 relative is the stated bar; we hold 1e-9 (only exp() differs)"""
+    xs, ys = seqbufs(x, reads)
+    r = G.backward_counts(cfg, xi, yi, per_pair=True)
+    oc = oracle_cfg(cfg)
+    tot = np.zeros_like(r["counts"])
+    for p, (a, b) in enumerate(zip(xi, yi)):
+        o = O.backward(xs[a], ys[b], s_or, oc)
+        assert o["fwd"] == r["fwd"][p] or (np.isinf(o["fwd"]) and np.isinf(r["fwd"][p]))
+        if np.isfinite(o["fwd"]):
+            assert abs(o["back"] - r["back"][p]) <= 1e-9 * abs(o["back"]), (p, o["back"], r["back"][p])
+            np.testing.assert_allclose(r["counts_per_pair"][p], o["counts"], rtol=rel, atol=1e-12)
+            tot += o["counts"]
+    np.testing.assert_allclose(r["counts"], tot, rtol=rel, atol=1e-12)
+    return r
