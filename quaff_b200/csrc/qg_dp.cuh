@@ -307,12 +307,9 @@ __global__ void qg_forward_finalize_kernel (const qg_pair_dp* __restrict__ pairs
   result[p] = end;
 }
 
-// Viterbi: pick the end cell (max, ties -> largest i, qmodel.cpp:1565-1575), then follow the pointers.
-// One thread per pair; ops are written back-to-front into the pair's scratch region.
-__global__ void qg_traceback_kernel (const qg_pair_dp* __restrict__ pairs, uint32_t npairs, const qg_segment* __restrict__ segs,
-                                     const double* __restrict__ seg_end, const uint32_t* __restrict__ trace,
-                                     double* __restrict__ score, uint32_t* __restrict__ x_start, uint32_t* __restrict__ x_end,
-                                     uint8_t* __restrict__ path_scratch, uint32_t* __restrict__ path_len, uint32_t* __restrict__ err_flag) {
+// Viterbi result per pair: the end cell (max, ties -> largest i, qmodel.cpp:1565-1575) over the pair's segments
+__global__ void qg_pair_score_kernel (const qg_pair_dp* __restrict__ pairs, uint32_t npairs, const double* __restrict__ seg_end,
+                                      double* __restrict__ score, uint32_t* __restrict__ x_end) {
   const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= npairs) return;
   const qg_pair_dp pd = pairs[p];
@@ -322,9 +319,21 @@ __global__ void qg_traceback_kernel (const qg_pair_dp* __restrict__ pairs, uint3
     if (sc > best || (sc == best && si > bi)) { best = sc; bi = si; }
   }
   score[p] = best;
-  x_start[p] = 0; x_end[p] = 0; path_len[p] = 0;
-  if (!pd.want_path || !(best > QG_NEG_INF)) return;
-  int i = bi, j = (int) pd.ylen;
+  x_end[p] = (best > QG_NEG_INF) ? (uint32_t) bi : 0u;
+}
+
+// Follow the pointers from the end cell.  One thread per pair; ops are written back-to-front into the pair's
+// scratch region (state sequence of qmodel.cpp:1579-1622).
+__global__ void qg_traceback_kernel (const qg_pair_dp* __restrict__ pairs, uint32_t npairs, const qg_segment* __restrict__ segs,
+                                     const uint32_t* __restrict__ trace, const double* __restrict__ score, const uint32_t* __restrict__ x_end,
+                                     uint32_t* __restrict__ x_start, uint8_t* __restrict__ path_scratch, uint32_t* __restrict__ path_len,
+                                     uint32_t* __restrict__ err_flag) {
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= npairs) return;
+  const qg_pair_dp pd = pairs[p];
+  x_start[p] = 0; path_len[p] = 0;
+  if (!pd.want_path || !(score[p] > QG_NEG_INF)) return;
+  int i = (int) x_end[p], j = (int) pd.ylen;
   int state = 1;                                           // 0 Start, 1 Match, 2 Insert, 3 Delete
   uint32_t n = 0;
   uint32_t cs = pd.seg_begin;
@@ -359,7 +368,6 @@ __global__ void qg_traceback_kernel (const qg_pair_dp* __restrict__ pairs, uint3
     if (i < 0 || j < 0) { *err_flag = 3; break; }
   }
   x_start[p] = (uint32_t) (i + 1);
-  x_end[p] = (uint32_t) bi;
   path_len[p] = n;
 }
 

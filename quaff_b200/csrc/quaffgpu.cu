@@ -531,10 +531,11 @@ static uint64_t qg_plan_cells (const qg_env_result& er, size_t p0, size_t p1) {
 }
 
 // ---- Viterbi -------------------------------------------------------------------------------------------------------
-extern "C" int qg_viterbi (qg_ctx* ctx, const qg_dpconfig* cfg, size_t n_pairs, const uint32_t* xi, const uint32_t* yi,
-                           const uint8_t* want_path, double* score, uint32_t* x_start, uint32_t* x_end,
-                           uint8_t** path_out, uint64_t* path_offsets) {
-  if (!ctx || !cfg || !xi || !yi || !score) return QG_ERR_INVALID;
+// group > 0: pairs come in consecutive groups of `group` (one read against every reference); the traceback then
+// runs only for the best-scoring pair of each group, earliest index on ties (qmodel.cpp:2773-2775).
+static int qg_viterbi_impl (qg_ctx* ctx, const qg_dpconfig* cfg, size_t n_pairs, const uint32_t* xi, const uint32_t* yi,
+                            const uint8_t* want_path, size_t group, double* score, uint32_t* x_start, uint32_t* x_end,
+                            uint8_t** path_out, uint64_t* path_offsets) {
   QG_TRY (qg_check_ready (ctx, cfg));
   const bool paths = path_out && path_offsets && x_start && x_end;
   if (path_out) *path_out = nullptr;
@@ -548,37 +549,38 @@ extern "C" int qg_viterbi (qg_ctx* ctx, const qg_dpconfig* cfg, size_t n_pairs, 
   std::vector<uint8_t> all_paths;
   std::vector<uint64_t> offs (n_pairs + 1, 0);
   uint64_t path_total = 0;
+  const size_t step = group ? group : 1;
   size_t p0 = 0;
   while (p0 < n_pairs) {
-    // grow the batch while the trace fits
     size_t p1 = p0; uint64_t words = 0;
     while (p1 < n_pairs) {
       uint64_t w = 0;
-      for (uint32_t r = er.run_begin[p1]; r < er.run_begin[p1 + 1]; ++r) {
-        int R, nw; const uint32_t width = (uint32_t) (er.runs[r].y - er.runs[r].x + 1);
-        if (qg_pick_R (width, &R, &nw) != QG_OK) QG_FAIL (ctx, QG_ERR_UNSUPPORTED, "pair %zu: a run of %u consecutive diagonals exceeds the %d this build fills with one CTA", p1, width, 256 * QG_MAX_NW);
-        w += ((uint64_t) ctx->seqs[QG_READS].len (yi[p1]) + 32ull * nw + 1) * 32ull * nw;
-      }
+      const size_t pe = std::min (n_pairs, p1 + step);
+      for (size_t q = p1; q < pe; ++q)
+        for (uint32_t r = er.run_begin[q]; r < er.run_begin[q + 1]; ++r) {
+          int R, nw; const uint32_t width = (uint32_t) (er.runs[r].y - er.runs[r].x + 1);
+          if (qg_pick_R (width, &R, &nw) != QG_OK) QG_FAIL (ctx, QG_ERR_UNSUPPORTED, "pair %zu: a run of %u consecutive diagonals exceeds the %d this build fills with one CTA", q, width, 256 * QG_MAX_NW);
+          w += ((uint64_t) ctx->seqs[QG_READS].len (yi[q]) + 32ull * nw + 1) * 32ull * nw;
+        }
       if (p1 > p0 && (words + w) * 4 > budget) break;
-      words += w; ++p1;
+      words += w; p1 = pe;
     }
     qg_dp_plan plan;
     QG_TRY (qg_build_plan (ctx, er, p0, p1, xi, yi, QG_REFS, 0, plan));
     const size_t np = p1 - p0;
-    uint64_t scratch_bytes = 0;
-    for (size_t p = 0; p < np; ++p) {
-      plan.pairs[p].want_path = paths && (!want_path || want_path[p0 + p]) ? 1 : 0;
-      plan.pairs[p].path_off = scratch_bytes;
-      if (plan.pairs[p].want_path) scratch_bytes += plan.pairs[p].path_cap;
-    }
     for (uint32_t s : plan.order) plan.segs_sorted.push_back (plan.segs[s]);
-    // seg_end is indexed by launch order (blockIdx of the class launch + class begin) -> remap per pair below
     {
       qg_timer tm (ctx, &ctx->stats.ms_prep);
       QG_TRY (qg_stage_rowparams (ctx, plan));
       QG_TRY (qg_upload (ctx, ctx->scratch[SC_SEGS], plan.segs_sorted.data (), sizeof (qg_segment) * plan.segs_sorted.size ()));
+      QG_TRY (qg_upload (ctx, ctx->scratch[SC_MISC0], plan.segs.data (), sizeof (qg_segment) * plan.segs.size ()));
       QG_TRY (qg_reserve (ctx, ctx->scratch[SC_TRACE], sizeof (uint32_t) * (plan.trace_words + 1)));
       QG_TRY (qg_reserve (ctx, ctx->scratch[SC_ENDVALS], sizeof (double) * 2 * (plan.segs.size () + 1)));
+      QG_TRY (qg_upload (ctx, ctx->scratch[SC_PAIRDP], plan.pairs.data (), sizeof (qg_pair_dp) * np));
+      QG_TRY (qg_reserve (ctx, ctx->scratch[SC_OUT0], sizeof (double) * (np + 1)));
+      QG_TRY (qg_reserve (ctx, ctx->scratch[SC_OUT1], sizeof (uint32_t) * (np + 1)));
+      QG_TRY (qg_reserve (ctx, ctx->scratch[SC_OUT2], sizeof (uint32_t) * (np + 1)));
+      QG_TRY (qg_reserve (ctx, ctx->scratch[SC_OUT3], sizeof (uint32_t) * (np + 1)));
     }
     ctx->stats.trace_bytes += plan.trace_words * 4;
     ctx->stats.n_segments += plan.segs.size ();
@@ -589,37 +591,61 @@ extern "C" int qg_viterbi (qg_ctx* ctx, const qg_dpconfig* cfg, size_t n_pairs, 
       a.trace = ctx->scratch[SC_TRACE].as<uint32_t> ();
       a.endvals = ctx->scratch[SC_ENDVALS].as<double> ();       // {score, i} per segment, indexed by seg.aux_off (pair order)
       QG_TRY (qg_launch_fill<0> (ctx, plan, a, ctx->scratch[SC_SEGS].as<qg_segment> ()));
+      QG_LAUNCH (qg_pair_score_kernel, (unsigned) ((np + 127) / 128), 128, 0, ctx->stream,
+                 ctx->scratch[SC_PAIRDP].as<qg_pair_dp> (), (uint32_t) np, ctx->scratch[SC_ENDVALS].as<double> (),
+                 ctx->scratch[SC_OUT0].as<double> (), ctx->scratch[SC_OUT2].as<uint32_t> ());
+      QG_TRY (qg_check_launch (ctx, "qg_pair_score_kernel"));
     }
-    {
-      qg_timer tm (ctx, &ctx->stats.ms_traceback);
-      QG_TRY (qg_upload (ctx, ctx->scratch[SC_MISC0], plan.segs.data (), sizeof (qg_segment) * plan.segs.size ()));
-      QG_TRY (qg_upload (ctx, ctx->scratch[SC_PAIRDP], plan.pairs.data (), sizeof (qg_pair_dp) * np));
-      QG_TRY (qg_reserve (ctx, ctx->scratch[SC_OUT0], sizeof (double) * (np + 1)));
-      QG_TRY (qg_reserve (ctx, ctx->scratch[SC_OUT1], sizeof (uint32_t) * (np + 1)));
-      QG_TRY (qg_reserve (ctx, ctx->scratch[SC_OUT2], sizeof (uint32_t) * (np + 1)));
-      QG_TRY (qg_reserve (ctx, ctx->scratch[SC_OUT3], sizeof (uint32_t) * (np + 1)));
-      QG_TRY (qg_reserve (ctx, ctx->scratch[SC_PATHSCR], scratch_bytes + 16));
-      QG_CUDA (ctx, cudaMemsetAsync (ctx->scratch[SC_FLAGS].p, 0, 64, ctx->stream));
-      QG_LAUNCH (qg_traceback_kernel, (unsigned) ((np + 63) / 64), 64, 0, ctx->stream,
-                 ctx->scratch[SC_PAIRDP].as<qg_pair_dp> (), (uint32_t) np, ctx->scratch[SC_MISC0].as<qg_segment> (),
-                 ctx->scratch[SC_ENDVALS].as<double> (), ctx->scratch[SC_TRACE].as<uint32_t> (),
-                 ctx->scratch[SC_OUT0].as<double> (), ctx->scratch[SC_OUT1].as<uint32_t> (), ctx->scratch[SC_OUT2].as<uint32_t> (),
-                 ctx->scratch[SC_PATHSCR].as<uint8_t> (), ctx->scratch[SC_OUT3].as<uint32_t> (), (uint32_t*) ctx->scratch[SC_FLAGS].p);
-      QG_TRY (qg_check_launch (ctx, "qg_traceback_kernel"));
-    }
-    std::vector<uint32_t> plen (np), xs (np), xe (np);
-    uint32_t flag = 0;
     {
       qg_timer tm (ctx, &ctx->stats.ms_d2h);
       QG_TRY (qg_download (ctx, score + p0, ctx->scratch[SC_OUT0].p, sizeof (double) * np));
-      QG_TRY (qg_download (ctx, xs.data (), ctx->scratch[SC_OUT1].p, sizeof (uint32_t) * np));
-      QG_TRY (qg_download (ctx, xe.data (), ctx->scratch[SC_OUT2].p, sizeof (uint32_t) * np));
-      QG_TRY (qg_download (ctx, plen.data (), ctx->scratch[SC_OUT3].p, sizeof (uint32_t) * np));
-      QG_TRY (qg_download (ctx, &flag, ctx->scratch[SC_FLAGS].p, sizeof (uint32_t)));
     }
-    if (flag) QG_FAIL (ctx, QG_ERR_CUDA, "internal: traceback left the envelope (code %u)", flag);
-    if (x_start) for (size_t p = 0; p < np; ++p) { x_start[p0 + p] = xs[p]; x_end[p0 + p] = xe[p]; }
     if (paths) {
+      // which pairs get a traceback
+      uint64_t scratch_bytes = 0;
+      for (size_t p = 0; p < np; ++p) plan.pairs[p].want_path = 0;
+      if (group) {
+        for (size_t g0 = 0; g0 < np; g0 += group) {
+          size_t best = g0; bool any = false;
+          for (size_t q = g0; q < std::min (np, g0 + group); ++q) {
+            const double sc = score[p0 + q];
+            if (sc > -INFINITY && (!any || sc > score[p0 + best])) { best = q; any = true; }
+          }
+          if (any) plan.pairs[best].want_path = 1;
+        }
+      } else {
+        for (size_t p = 0; p < np; ++p) plan.pairs[p].want_path = (!want_path || want_path[p0 + p]) ? 1 : 0;
+      }
+      for (size_t p = 0; p < np; ++p) {
+        plan.pairs[p].path_off = scratch_bytes;
+        if (plan.pairs[p].want_path) scratch_bytes += plan.pairs[p].path_cap;
+      }
+      std::vector<uint32_t> plen (np), xs (np), xe (np);
+      uint32_t flag = 0;
+      {
+        qg_timer tm (ctx, &ctx->stats.ms_traceback);
+        QG_TRY (qg_upload (ctx, ctx->scratch[SC_PAIRDP], plan.pairs.data (), sizeof (qg_pair_dp) * np));
+        QG_TRY (qg_reserve (ctx, ctx->scratch[SC_PATHSCR], scratch_bytes + 16));
+        QG_CUDA (ctx, cudaMemsetAsync (ctx->scratch[SC_FLAGS].p, 0, 64, ctx->stream));
+        QG_LAUNCH (qg_traceback_kernel, (unsigned) ((np + 63) / 64), 64, 0, ctx->stream,
+                   ctx->scratch[SC_PAIRDP].as<qg_pair_dp> (), (uint32_t) np, ctx->scratch[SC_MISC0].as<qg_segment> (),
+                   ctx->scratch[SC_TRACE].as<uint32_t> (), ctx->scratch[SC_OUT0].as<double> (), ctx->scratch[SC_OUT2].as<uint32_t> (),
+                   ctx->scratch[SC_OUT1].as<uint32_t> (), ctx->scratch[SC_PATHSCR].as<uint8_t> (), ctx->scratch[SC_OUT3].as<uint32_t> (),
+                   (uint32_t*) ctx->scratch[SC_FLAGS].p);
+        QG_TRY (qg_check_launch (ctx, "qg_traceback_kernel"));
+      }
+      {
+        qg_timer tm (ctx, &ctx->stats.ms_d2h);
+        QG_TRY (qg_download (ctx, xs.data (), ctx->scratch[SC_OUT1].p, sizeof (uint32_t) * np));
+        QG_TRY (qg_download (ctx, xe.data (), ctx->scratch[SC_OUT2].p, sizeof (uint32_t) * np));
+        QG_TRY (qg_download (ctx, plen.data (), ctx->scratch[SC_OUT3].p, sizeof (uint32_t) * np));
+        QG_TRY (qg_download (ctx, &flag, ctx->scratch[SC_FLAGS].p, sizeof (uint32_t)));
+      }
+      if (flag) QG_FAIL (ctx, QG_ERR_CUDA, "internal: traceback left the envelope (code %u)", flag);
+      for (size_t p = 0; p < np; ++p) {
+        const bool w = plan.pairs[p].want_path != 0;
+        x_start[p0 + p] = w ? xs[p] : 0; x_end[p0 + p] = w ? xe[p] : 0;
+      }
       std::vector<uint64_t> goff (np + 1, 0);
       for (size_t p = 0; p < np; ++p) goff[p + 1] = goff[p] + plen[p];
       for (size_t p = 0; p < np; ++p) offs[p0 + p] = path_total + goff[p];
@@ -646,6 +672,53 @@ extern "C" int qg_viterbi (qg_ctx* ctx, const qg_dpconfig* cfg, size_t n_pairs, 
     if (path_total) memcpy (buf, all_paths.data (), path_total);
     *path_out = buf;
   }
+  return QG_OK;
+}
+
+extern "C" int qg_viterbi (qg_ctx* ctx, const qg_dpconfig* cfg, size_t n_pairs, const uint32_t* xi, const uint32_t* yi,
+                           const uint8_t* want_path, double* score, uint32_t* x_start, uint32_t* x_end,
+                           uint8_t** path_out, uint64_t* path_offsets) {
+  if (!ctx || !cfg || !xi || !yi || !score) return QG_ERR_INVALID;
+  return qg_viterbi_impl (ctx, cfg, n_pairs, xi, yi, want_path, 0, score, x_start, x_end, path_out, path_offsets);
+}
+
+// ---- seam A: QuaffAligner::align (qmodel.cpp:2624-2646) = QuaffAlignmentTask::run for every read (qmodel.cpp:2764-2778)
+extern "C" int qg_align_reads (qg_ctx* ctx, const qg_dpconfig* cfg, const double* null_loglike,
+                               uint32_t* best_ref, double* score, uint32_t* x_start, uint32_t* x_end,
+                               uint8_t** path_out, uint64_t* path_offsets) {
+  if (!ctx || !cfg || !null_loglike || !best_ref || !score || !x_start || !x_end || !path_out || !path_offsets) return QG_ERR_INVALID;
+  QG_TRY (qg_check_ready (ctx, cfg));
+  const size_t nx = ctx->seqs[QG_REFS].n, ny = ctx->seqs[QG_READS].n;
+  const size_t np = nx * ny;
+  std::vector<uint32_t> xi (np), yi (np);
+  for (size_t y = 0; y < ny; ++y) for (size_t x = 0; x < nx; ++x) { xi[y * nx + x] = (uint32_t) x; yi[y * nx + x] = (uint32_t) y; }
+  std::vector<double> sc (np);
+  std::vector<uint32_t> xs (np), xe (np);
+  std::vector<uint64_t> poff (np + 1);
+  uint8_t* paths = nullptr;
+  QG_TRY (qg_viterbi_impl (ctx, cfg, np, xi.data (), yi.data (), nullptr, nx, sc.data (), xs.data (), xe.data (), &paths, poff.data ()));
+  // the traced pair of each read is its best one; compact the path list to one entry per read
+  uint64_t total = 0;
+  for (size_t y = 0; y < ny; ++y) {
+    best_ref[y] = 0xFFFFFFFFu; score[y] = -INFINITY; x_start[y] = 0; x_end[y] = 0;
+    path_offsets[y] = total;
+    size_t best = 0; bool any = false;
+    for (size_t x = 0; x < nx; ++x) {
+      const double v = sc[y * nx + x];
+      if (v > -INFINITY && (!any || v > sc[y * nx + best])) { best = x; any = true; }
+    }
+    if (any) {
+      const size_t p = y * nx + best;
+      best_ref[y] = (uint32_t) best;
+      score[y] = sc[p] - null_loglike[y];                       // scoreAdjustedAlignment, qmodel.cpp:1648-1654
+      x_start[y] = xs[p]; x_end[y] = xe[p];
+      const uint64_t len = poff[p + 1] - poff[p];
+      memmove (paths + total, paths + poff[p], len);            // total <= poff[p]: compaction moves data towards the front
+      total += len;
+    }
+  }
+  path_offsets[ny] = total;
+  *path_out = paths;
   return QG_OK;
 }
 
@@ -804,5 +877,85 @@ extern "C" int qg_backward_counts (qg_ctx* ctx, const qg_dpconfig* cfg, size_t n
   }
   if (counts_sum) { qg_timer tm (ctx, &ctx->stats.ms_d2h); QG_TRY (qg_download (ctx, counts_sum, dSum.p, sizeof (double) * nC)); }
   QG_CUDA (ctx, cudaStreamSynchronize (ctx->stream));
+  return QG_OK;
+}
+
+// ---- seam C: QuaffTrainer::getCounts (qmodel.cpp:2005-2032) = QuaffCountingTask::run per read (qmodel.cpp:2238-2271) ----
+// The DP runs on the device; what stays here is the reference's per-read control flow: the order-dependent
+// "F >= yLL - 20" gate, the posterior weights and the pruning of sortOrder.
+static double qg_host_lse (const std::vector<double>& tab, double a, double b) {     // logsumexp.cpp:34-59, 84-103
+  double mx, diff;
+  if (a == b) { mx = a; diff = 0; } else if (a < b) { mx = b; diff = b - a; } else { mx = a; diff = a - b; }
+  double u = 0;
+  if (!(diff >= 10.0 || std::isnan (diff) || std::isinf (diff))) {
+    const int n = (int) (diff / .0001);
+    const double dx = diff - (n * .0001);
+    const double f0 = tab[n], f1 = tab[n + 1];
+    u = f0 + (f1 - f0) * (dx / .0001);
+  }
+  return mx + u;
+}
+
+extern "C" int qg_estep (qg_ctx* ctx, const qg_dpconfig* cfg, int use_null, const double* null_loglike,
+                         uint32_t* sort_order, uint32_t* sort_len, double* y_loglike,
+                         double* param_counts, double* loglike_sum) {
+  if (!ctx || !cfg || !sort_order || !sort_len || !y_loglike || !param_counts || !loglike_sum) return QG_ERR_INVALID;
+  if (use_null && !null_loglike) QG_FAIL (ctx, QG_ERR_INVALID, "qg_estep: use_null without null_loglike");
+  QG_TRY (qg_check_ready (ctx, cfg));
+  const size_t nx = ctx->seqs[QG_REFS].n, ny = ctx->seqs[QG_READS].n;
+  const int mk = ctx->model.match_k, gk = ctx->model.gap_k;
+  const uint64_t nK = qg_pow4 (mk), nG = qg_pow4 (gk), nC = qg_counts_size (mk, gk);
+  std::vector<double> tab (100002);
+  { const int n = ((int) (10 / .0001)) + 1; for (int t = 0; t < n; ++t) { const double x = t * .0001; tab[t] = log (1. + exp (-x)); } tab[n] = 0; }
+
+  // 1. Forward for every (read, ref in sortOrder) pair
+  std::vector<uint32_t> xi, yi; std::vector<size_t> first (ny + 1);
+  for (size_t y = 0; y < ny; ++y) {
+    first[y] = xi.size ();
+    if (sort_len[y] > nx) QG_FAIL (ctx, QG_ERR_INVALID, "qg_estep: sort_len[%zu] > number of references", y);
+    for (uint32_t s = 0; s < sort_len[y]; ++s) {
+      const uint32_t n = sort_order[y * nx + s];
+      if (n >= nx) QG_FAIL (ctx, QG_ERR_INVALID, "qg_estep: sort_order entry out of range");
+      xi.push_back (n); yi.push_back ((uint32_t) y);
+    }
+  }
+  first[ny] = xi.size ();
+  std::vector<double> F (xi.size ());
+  if (!xi.empty ()) QG_TRY (qg_forward (ctx, cfg, xi.size (), xi.data (), yi.data (), F.data ()));
+
+  // 2. replay the gate in sortOrder order; collect the pairs that need Backward
+  std::vector<uint32_t> bxi, byi; std::vector<double> bw;
+  std::vector<std::vector<double> > xyLL (ny, std::vector<double> (nx, -INFINITY));
+  *loglike_sum = 0;
+  for (size_t y = 0; y < ny; ++y) {
+    double yLL = use_null ? null_loglike[y] : -INFINITY;
+    std::vector<size_t> gated;
+    for (size_t p = first[y]; p < first[y + 1]; ++p) {
+      xyLL[y][xi[p]] = F[p];
+      if (F[p] >= yLL - 20) gated.push_back (p);                  // MAX_TRAINING_LOG_DELTA, qmodel.cpp:23, 2252
+      yLL = qg_host_lse (tab, yLL, F[p]);
+    }
+    for (size_t p : gated) { bxi.push_back (xi[p]); byi.push_back ((uint32_t) y); bw.push_back (exp (F[p] - yLL)); }
+    y_loglike[y] = yLL;
+    *loglike_sum += yLL;                                          // accumulate(yLogLike, 0.), qmodel.cpp:2420-2422
+    // sortOrder := refs by descending F, cut at the first one below yLL - 20 (qmodel.cpp:2264-2270)
+    std::vector<size_t> idx (nx);
+    std::iota (idx.begin (), idx.end (), (size_t) 0);
+    const std::vector<double>& v = xyLL[y];
+    std::sort (idx.begin (), idx.end (), [&] (size_t a, size_t b) { return v[a] < v[b]; });
+    uint32_t len = 0;
+    for (size_t t = nx; t-- > 0; ) { if (v[idx[t]] < yLL - 20) break; sort_order[y * nx + len++] = (uint32_t) idx[t]; }
+    sort_len[y] = len;
+  }
+
+  // 3. Backward on the gated pairs, posterior-weighted sum of QuaffCounts, then QuaffParamCounts (qmodel.cpp:407-417)
+  std::vector<double> qc (nC, 0.0);
+  if (!bxi.empty ()) QG_TRY (qg_backward_counts (ctx, cfg, bxi.size (), bxi.data (), byi.data (), bw.data (), nullptr, nullptr, qc.data (), nullptr));
+  const size_t nEmit = 4 * nK * QG_NQUAL + 4 * QG_NQUAL;
+  memcpy (param_counts, qc.data (), sizeof (double) * nEmit);
+  const double *m2m = qc.data () + nEmit, *m2i = m2m + nG, *m2d = m2i + nG, *m2e = m2d + nG, *sc = m2e + nG;
+  double *bINo = param_counts + nEmit, *bIYes = bINo + nG, *bDNo = bIYes + nG, *bDYes = bDNo + nG, *ext = bDYes + nG;
+  for (uint64_t g = 0; g < nG; ++g) { bINo[g] = m2m[g] + m2d[g]; bIYes[g] = m2i[g] + m2e[g]; bDNo[g] = m2m[g]; bDYes[g] = m2d[g]; }
+  ext[0] = sc[3]; ext[1] = sc[2]; ext[2] = sc[1]; ext[3] = sc[0];     // extendInsertNo=i2m, Yes=i2i, extendDeleteNo=d2m, Yes=d2d
   return QG_OK;
 }

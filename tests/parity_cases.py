@@ -96,3 +96,19 @@ def check_backward(G, O, x, reads, s_or, cfg, xi, yi, rel=1e-9):
             tot += o["counts"]
     np.testing.assert_allclose(r["counts"], tot, rtol=rel, atol=1e-12)
     return r
+
+
+def check_estep(G, O, x, reads, s_or, nullp, cfg, use_null=True, n_iter=2, rel=1e-9):
+    """QuaffCountingTask::run replayed over `n_iter` E-steps (sortOrder pruning carried across)."""
+    xs, ys = seqbufs(x, reads)
+    null_ll = np.array([api.null_loglike(nullp, r, G.L) for r in reads])
+    so_g = so_o = None
+    for it in range(n_iter):
+        g = G.estep(cfg, use_null, null_ll, so_g)
+        o = O.estep(xs, ys, s_or, nullp, use_null, oracle_cfg(cfg), so_o)
+        np.testing.assert_allclose(g["y_loglike"], o["loglike"], rtol=1e-12)
+        assert g["sort_order"] == o["sort_order"], (it, g["sort_order"], o["sort_order"])
+        np.testing.assert_allclose(g["counts"], o["counts"], rtol=rel, atol=1e-12)
+        assert abs(g["loglike"] - o["loglike"].sum()) <= 1e-9 * abs(g["loglike"])
+        so_g, so_o = g["sort_order"], o["sort_order"]
+    return g

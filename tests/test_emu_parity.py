@@ -40,3 +40,26 @@ def test_emu_backward_counts(emu, oracle, workload):
     x, reads, s_or = workload
     xi, yi = pc.all_pairs(len(x), len(reads))
     pc.check_backward(emu, oracle, x, reads, s_or, api.dp_config(kmer_threshold=6), xi, yi)
+
+
+def test_emu_align_reads_and_estep(emu, oracle, workload):
+    from quaff_b200.params import QuaffNullParams
+    import os
+    x, reads, s_or = workload
+    nullp = QuaffNullParams.load(os.path.join(os.path.dirname(__file__), "golden", "testquaffnullparams.json"))
+    cfg = api.dp_config(kmer_threshold=6)
+    pc.check_estep(emu, oracle, x, reads, s_or, nullp, cfg, use_null=True, n_iter=2)
+    # seam A: best reference per read, null-adjusted score
+    null_ll = np.array([api.null_loglike(nullp, r, emu.L) for r in reads])
+    a = emu.align_reads(cfg, null_ll)
+    xs, ys = pc.seqbufs(x, reads)
+    for m in range(len(reads)):
+        best, bo = None, None
+        for n in range(len(x)):
+            o = oracle.viterbi(xs[n], ys[m], s_or, pc.oracle_cfg(cfg))
+            if np.isfinite(o["result"]) and (bo is None or o["result"] > bo["result"]):
+                best, bo = n, o
+        assert a["best_ref"][m] == best
+        assert a["score"][m] == bo["result"] - null_ll[m]
+        assert a["x_start"][m] == bo["x_start"] and a["x_end"][m] == bo["x_end"]
+        assert np.array_equal(a["paths"][m], bo["path"])
