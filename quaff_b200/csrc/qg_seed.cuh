@@ -27,8 +27,13 @@ struct qg_pair_desc {
   uint32_t xseq, yseq, xlen, ylen;
   uint64_t xoff, yoff;               // position offsets into the code / token arrays
   uint32_t item_begin, item_end;     // this pair's items (empty when the envelope is full)
-  uint32_t full;                     // 1 = initFull (diagenv.cpp:11-18, 23-29)
+  uint32_t full;                     // 1 = initFull (diagenv.cpp:11-18, 23-29); 2 = memory-guided, runs already in pair_runs
   uint32_t run_out;                  // offset of this pair's merged runs in pair_runs
+  uint32_t run_cap;                  // memory-guided mode: capacity of that region
+  uint32_t pad_;
+  uint64_t count_off;                // memory-guided mode: offset of this pair's per-diagonal counts
+  uint64_t bits_off;                 // memory-guided mode: word offset of this pair's three bitmaps
+  uint64_t hist_off;                 // memory-guided mode: offset of this pair's count histogram
 };
 
 // ---- 2-bit packing + k-mer codes ----------------------------------------------------------------
@@ -70,7 +75,7 @@ qg_seed_kernel (const qg_seed_item* __restrict__ items, const qg_pair_desc* __re
                 const uint16_t* __restrict__ xcodes, const uint16_t* __restrict__ ycodes,
                 int k, int threshold, int half_band, uint32_t ring, uint32_t ymax, uint32_t run_cap,
                 int2* __restrict__ item_runs, uint32_t* __restrict__ item_nruns, unsigned long long* __restrict__ hit_counter,
-                uint32_t* __restrict__ overflow_flag) {
+                uint32_t* __restrict__ overflow_flag, uint32_t* __restrict__ counts_out) {
   QG_DYN_SMEM (smem);
   const uint32_t nk = 1u << (2 * k);
   uint32_t* cnt = (uint32_t*) smem;
@@ -152,7 +157,10 @@ qg_seed_kernel (const qg_seed_item* __restrict__ items, const qg_pair_desc* __re
         for (int g = wid; g < gcount; g += QG_SEED_THREADS / 32) {
           const int d = emit_lo + (g0 + g) * 32 + lane;
           uint32_t c = 0;
-          if (d < emit_hi) { const uint32_t idx = (uint32_t) (d + ylen) & mask; c = cnt[idx]; cnt[idx] = 0; }
+          if (d < emit_hi) {
+            const uint32_t idx = (uint32_t) (d + ylen) & mask; c = cnt[idx]; cnt[idx] = 0;
+            if (counts_out) { counts_out[pd.count_off + (uint64_t) (d + span)] = c; c = 0; }      // memory-guided mode: raw counts only
+          }
           const uint32_t m = __ballot_sync (QG_FULL_MASK, d < emit_hi && (int) c >= threshold && c > 0);
           if (lane == 0) { seedmask[g] = m; if (m) s_any = 1; }
         }
@@ -219,7 +227,9 @@ __global__ void qg_envelope_finalize_kernel (const qg_pair_desc* __restrict__ pa
   int2* out = pair_runs + pd.run_out;
   uint32_t n = 0, ndiag = 0;
   unsigned long long cu = 0;
-  if (pd.full) {
+  if (pd.full == 2) {
+    n = pair_info[p].x;                                     // runs were written by qg_memtier_kernel
+  } else if (pd.full) {
     out[0] = make_int2 (1 - ylen, xlen - 1);
     n = 1;
   } else {
@@ -243,6 +253,92 @@ __global__ void qg_envelope_finalize_kernel (const qg_pair_desc* __restrict__ pa
   for (uint32_t t = 0; t < n; ++t) { ndiag += (uint32_t) (out[t].y - out[t].x + 1); cu += qg_run_cells (out[t].x, out[t].y, xlen, ylen); }
   pair_info[p] = make_uint2 (n, ndiag);
   pair_cu[p] = cu;
+}
+
+
+// ---- memory-guided threshold (-kmatchmb / -kmatchmax): diagenv.cpp:62-96 with kmerThreshold < 0 -----------------
+// Count tiers are visited in descending order; a tier's seeds (all diagonals with exactly that count) are accepted
+// only if the storage diagonals of the enlarged envelope still fit: |storageDiags| * min(xLen,yLen) * cellSize < maxSize,
+// tested BEFORE accepting (so a budget smaller than one band leaves diagonal 0 alone).  One CTA per pair; rarely used,
+// so clarity over speed: two passes over the pair's per-diagonal counts per non-empty tier.
+__global__ void __launch_bounds__ (256)
+qg_memtier_kernel (const qg_pair_desc* __restrict__ pairs, const uint32_t* __restrict__ pair_ids, const uint32_t* __restrict__ counts,
+                   uint32_t* __restrict__ hist_all, uint32_t* __restrict__ bits_all, int k, int half_band,
+                   unsigned long long cell_size, unsigned long long max_size,
+                   int2* __restrict__ pair_runs, uint2* __restrict__ pair_info, uint32_t* __restrict__ overflow_flag) {
+  __shared__ uint32_t s_cmax, s_new;
+  __shared__ unsigned long long s_nstorage;
+  __shared__ int s_stop;
+  const uint32_t p = pair_ids[blockIdx.x];
+  const qg_pair_desc pd = pairs[p];
+  const int xlen = (int) pd.xlen, ylen = (int) pd.ylen;
+  const int span = ylen - k;
+  const int ndiag = (xlen - k) + span + 1;                  // diagonals that can receive hits: d = t - span
+  const uint32_t* cnt = counts + pd.count_off;
+  uint32_t* hist = hist_all + pd.hist_off;                  // [ylen + 2]
+  const int nbits = xlen + ylen + 3;                        // bit index = d + ylen + 1, d in [-ylen-1, xlen+1]
+  const int nwords = (nbits + 31) / 32;
+  uint32_t* accepted = bits_all + pd.bits_off;
+  uint32_t* trial = accepted + nwords;
+  uint32_t* env = trial + nwords;
+  const int min_diag = 1 - ylen, max_diag = xlen - 1;
+  const unsigned long long diag_size = (unsigned long long) (xlen < ylen ? xlen : ylen) * cell_size;
+  const int tid = threadIdx.x;
+
+  for (int w = tid; w < 3 * nwords; w += blockDim.x) accepted[w] = 0;
+  for (int c = tid; c < ylen + 2; c += blockDim.x) hist[c] = 0;
+  if (tid == 0) { s_cmax = 0; s_new = 0; s_nstorage = 1; s_stop = 0; }
+  __syncthreads ();
+  for (int t = tid; t < ndiag; t += blockDim.x) { const uint32_t c = cnt[t]; if (c) { atomicAdd (&hist[c], 1u); atomicMax (&s_cmax, c); } }
+  if (tid == 0) { const int b = 0 + ylen + 1; accepted[b >> 5] |= 1u << (b & 31); env[b >> 5] |= 1u << (b & 31); }   // diags = storageDiags = {0}
+  __syncthreads ();
+  const uint32_t cmax = s_cmax;
+  for (uint32_t c = cmax; c >= 1; --c) {
+    if (hist[c] == 0) continue;
+    for (int t = tid; t < ndiag; t += blockDim.x)
+      if (cnt[t] == c) {
+        const int seed = t - span;
+        const int lo = (seed - half_band > min_diag ? seed - half_band : min_diag) - 1;
+        const int hi = (seed + half_band < max_diag ? seed + half_band : max_diag) + 1;
+        for (int d = lo; d <= hi; ++d) {
+          const int b = d + ylen + 1; const uint32_t bit = 1u << (b & 31);
+          if (!(accepted[b >> 5] & bit)) { const uint32_t old = atomicOr (&trial[b >> 5], bit); if (!(old & bit)) atomicAdd (&s_new, 1u); }
+        }
+      }
+    __syncthreads ();
+    if (tid == 0 && (s_nstorage + s_new) * diag_size >= max_size) s_stop = 1;      // diagenv.cpp:87-89
+    __syncthreads ();
+    if (s_stop) break;
+    for (int w = tid; w < nwords; w += blockDim.x) { accepted[w] |= trial[w]; trial[w] = 0; }
+    for (int t = tid; t < ndiag; t += blockDim.x)
+      if (cnt[t] == c) {
+        const int seed = t - span;
+        const int lo = seed - half_band > min_diag ? seed - half_band : min_diag;
+        const int hi = seed + half_band < max_diag ? seed + half_band : max_diag;
+        for (int d = lo; d <= hi; ++d) { const int b = d + ylen + 1; atomicOr (&env[b >> 5], 1u << (b & 31)); }
+      }
+    __syncthreads ();
+    if (tid == 0) { s_nstorage += s_new; s_new = 0; }
+    __syncthreads ();
+  }
+  __syncthreads ();
+  if (tid == 0) {
+    // envelope bitmap -> maximal runs, ascending
+    int2* out = pair_runs + pd.run_out;
+    uint32_t n = 0; int run_lo = 0; bool open = false;
+    for (int w = 0; w < nwords; ++w) {
+      const uint32_t v = env[w];
+      if (v == 0 && !open) continue;
+      for (int b = 0; b < 32; ++b) {
+        const bool set = (v >> b) & 1u;
+        const int d = w * 32 + b - ylen - 1;
+        if (set && !open) { run_lo = d; open = true; }
+        else if (!set && open) { if (n < pd.run_cap) out[n] = make_int2 (run_lo, d - 1); else *overflow_flag = 2; ++n; open = false; }
+      }
+    }
+    if (open) { if (n < pd.run_cap) out[n] = make_int2 (run_lo, nwords * 32 - 1 - ylen - 1); else *overflow_flag = 2; ++n; }
+    pair_info[p] = make_uint2 (n < pd.run_cap ? n : pd.run_cap, 0);
+  }
 }
 
 #endif

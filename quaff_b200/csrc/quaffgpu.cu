@@ -5,6 +5,7 @@
 #include "qg_seed.cuh"
 #include "qg_dp.cuh"
 #include "qg_backward.cuh"
+#include "qg_overlap.cuh"
 #include <map>
 #include <numeric>
 
@@ -250,7 +251,6 @@ struct qg_env_result {
 
 static int qg_envelope_stage_cap (qg_ctx* ctx, const qg_dpconfig* cfg, uint64_t cell_size, int x_set,
                                   size_t n_pairs, const uint32_t* xi, const uint32_t* yi, qg_env_result& out, uint32_t run_cap, bool* overflow) {
-  (void) cell_size;
   *overflow = false;
   const qg_seqset& X = ctx->seqs[x_set];
   const qg_seqset& Y = ctx->seqs[QG_READS];
@@ -258,6 +258,9 @@ static int qg_envelope_stage_cap (qg_ctx* ctx, const qg_dpconfig* cfg, uint64_t 
   std::vector<qg_pair_desc> pd (n_pairs);
   std::vector<qg_seed_item> items;
   bool any_sparse = false;
+  const bool memory_mode = cfg->kmer_threshold < 0;
+  std::vector<uint32_t> mem_pairs;
+  uint64_t count_total = 0, bits_total = 0, hist_total = 0;
   uint32_t ymax = 0;
   uint64_t run_total = 0;
   for (size_t p = 0; p < n_pairs; ++p) {
@@ -273,9 +276,9 @@ static int qg_envelope_stage_cap (qg_ctx* ctx, const qg_dpconfig* cfg, uint64_t 
     }
     d.full = full ? 1 : 0;
     d.item_begin = (uint32_t) items.size ();
+    d.run_cap = 0; d.pad_ = 0; d.count_off = 0; d.bits_off = 0; d.hist_off = 0;
+    uint64_t runs_here = 1;
     if (!full) {
-      if (cfg->kmer_threshold < 0)
-        QG_FAIL (ctx, QG_ERR_UNSUPPORTED, "memory-guided seeding (-kmatchmb/-kmatchmax) is handled by qg_envelope_memory_stage");
       if (d.xlen < (uint32_t) k || d.ylen < (uint32_t) k)
         QG_FAIL (ctx, QG_ERR_PRECONDITION, "pair %zu: sequence shorter than k=%d (the reference's KmerIndex underflows here, fastseq.cpp:247)", p, k);
       if (d.ylen > 65000) QG_FAIL (ctx, QG_ERR_UNSUPPORTED, "pair %zu: read of %u bases exceeds the 16-bit bucket index of the seeding kernel", p, d.ylen);
@@ -286,10 +289,20 @@ static int qg_envelope_stage_cap (qg_ctx* ctx, const qg_dpconfig* cfg, uint64_t 
         qg_seed_item it; it.pair = (uint32_t) p; it.d_begin = (int32_t) b; it.d_end = (int32_t) std::min<int64_t> (b + QG_SEED_CHUNK, dmax + 1);
         items.push_back (it);
       }
+      runs_here = (uint64_t) (items.size () - d.item_begin) * run_cap + 1;
+      if (memory_mode) {
+        d.full = 2;
+        mem_pairs.push_back ((uint32_t) p);
+        d.count_off = count_total; count_total += (uint64_t) d.xlen + d.ylen;
+        d.bits_off = bits_total; bits_total += 3ull * (((uint64_t) d.xlen + d.ylen + 3 + 31) / 32);
+        d.hist_off = hist_total; hist_total += (uint64_t) d.ylen + 2;
+        runs_here = ((uint64_t) d.xlen + d.ylen) / (2ull * ((unsigned) cfg->band_size / 2) + 2) + 4;
+        d.run_cap = (uint32_t) runs_here;
+      }
     }
     d.item_end = (uint32_t) items.size ();
     d.run_out = (uint32_t) run_total;
-    run_total += (uint64_t) (d.item_end - d.item_begin) * run_cap + 1;
+    run_total += runs_here;
     if (run_total > 0xFFFFFFF0ull) QG_FAIL (ctx, QG_ERR_UNSUPPORTED, "too many seeding work items in one call; split the pair list");
   }
   if (any_sparse && (k < 5 || k > 7)) QG_FAIL (ctx, QG_ERR_UNSUPPORTED, "-kmatch %d: this build's seeding kernel indexes k-mers of length 5..7 in shared memory", k);
@@ -306,6 +319,13 @@ static int qg_envelope_stage_cap (qg_ctx* ctx, const qg_dpconfig* cfg, uint64_t 
   QG_TRY (qg_reserve (ctx, dFL, 64));
   QG_CUDA (ctx, cudaMemsetAsync (dFL.p, 0, 64, ctx->stream));
 
+  if (memory_mode && !mem_pairs.empty ()) {
+    QG_TRY (qg_reserve (ctx, ctx->scratch[SC_STORE], sizeof (uint32_t) * (count_total + 1)));
+    QG_TRY (qg_reserve (ctx, ctx->scratch[SC_ROWACC], sizeof (uint32_t) * (hist_total + 1)));
+    QG_TRY (qg_reserve (ctx, ctx->scratch[SC_MISC1], sizeof (uint32_t) * (bits_total + 1)));
+    QG_TRY (qg_upload (ctx, ctx->scratch[SC_MISC0], mem_pairs.data (), sizeof (uint32_t) * mem_pairs.size ()));
+    QG_CUDA (ctx, cudaMemsetAsync (ctx->scratch[SC_STORE].p, 0, sizeof (uint32_t) * (count_total + 1), ctx->stream));
+  }
   if (!items.empty ()) {
     QG_TRY (qg_ensure_codes (ctx, x_set, k));
     QG_TRY (qg_ensure_codes (ctx, QG_READS, k));
@@ -321,8 +341,18 @@ static int qg_envelope_stage_cap (qg_ctx* ctx, const qg_dpconfig* cfg, uint64_t 
       QG_LAUNCH (qg_seed_kernel, (unsigned) items.size (), QG_SEED_THREADS, smem, ctx->stream,
                  dIT.as<qg_seed_item> (), dPD.as<qg_pair_desc> (), ctx->seqs[x_set].d_codes.as<uint16_t> (), ctx->seqs[QG_READS].d_codes.as<uint16_t> (),
                  k, cfg->kmer_threshold, (int) ((unsigned) cfg->band_size / 2), ring, ymax, run_cap,
-                 dIR.as<int2> (), dIN.as<uint32_t> (), (unsigned long long*) ((char*) dFL.p + 8), (uint32_t*) dFL.p);
+                 dIR.as<int2> (), dIN.as<uint32_t> (), (unsigned long long*) ((char*) dFL.p + 8), (uint32_t*) dFL.p,
+                 memory_mode ? ctx->scratch[SC_STORE].as<uint32_t> () : (uint32_t*) nullptr);
       QG_TRY (qg_check_launch (ctx, "qg_seed_kernel"));
+    }
+    if (memory_mode) {
+      qg_timer tm (ctx, &ctx->stats.ms_envelope);
+      QG_LAUNCH (qg_memtier_kernel, (unsigned) mem_pairs.size (), 256, 0, ctx->stream,
+                 dPD.as<qg_pair_desc> (), ctx->scratch[SC_MISC0].as<uint32_t> (), ctx->scratch[SC_STORE].as<uint32_t> (),
+                 ctx->scratch[SC_ROWACC].as<uint32_t> (), ctx->scratch[SC_MISC1].as<uint32_t> (), k, (int) ((unsigned) cfg->band_size / 2),
+                 (unsigned long long) cell_size, (unsigned long long) cfg->max_size,
+                 dPR.as<int2> (), dPI.as<uint2> (), (uint32_t*) dFL.p);
+      QG_TRY (qg_check_launch (ctx, "qg_memtier_kernel"));
     }
   }
   {
@@ -344,6 +374,7 @@ static int qg_envelope_stage_cap (qg_ctx* ctx, const qg_dpconfig* cfg, uint64_t 
     QG_TRY (qg_download (ctx, cu.data (), dPC.p, sizeof (unsigned long long) * n_pairs));
     QG_TRY (qg_download (ctx, pr.data (), dPR.p, sizeof (int2) * run_total));
   }
+  if ((uint32_t) flags[0] == 2) QG_FAIL (ctx, QG_ERR_CUDA, "internal: memory-guided envelope produced more runs than the bound");
   if ((uint32_t) flags[0]) { *overflow = true; return QG_OK; }
   ctx->stats.kmer_hits += flags[1];
   out.run_begin.resize (n_pairs + 1);
@@ -446,7 +477,8 @@ static int qg_build_plan (qg_ctx* ctx, const qg_env_result& er, size_t p0, size_
       sg.R = (uint32_t) R; sg.nwarps = (uint32_t) nw;
       sg.rp_off = it->second;
       const uint64_t lanes = 32ull * nw;
-      if (mode == 0) { sg.trace_off = plan.trace_words; plan.trace_words += ((uint64_t) pp.ylen + lanes + 1) * lanes; }
+      if (mode == 0 || mode == 3) { sg.trace_off = plan.trace_words; plan.trace_words += ((uint64_t) pp.ylen + lanes + 1) * lanes; }
+      if (mode == 3) { sg.acc_off = plan.acc_rows; plan.acc_rows += (uint64_t) pp.ylen + 2; }
       if (mode == 2) { sg.store_off = plan.store_doubles; plan.store_doubles += ((uint64_t) pp.ylen + 1) * 3 * lanes * R;
                        sg.acc_off = plan.acc_rows; plan.acc_rows += (uint64_t) pp.ylen + 2; }
       sg.seg_id = plan.segs.size ();
@@ -957,5 +989,294 @@ extern "C" int qg_estep (qg_ctx* ctx, const qg_dpconfig* cfg, int use_null, cons
   double *bINo = param_counts + nEmit, *bIYes = bINo + nG, *bDNo = bIYes + nG, *bDYes = bDNo + nG, *ext = bDYes + nG;
   for (uint64_t g = 0; g < nG; ++g) { bINo[g] = m2m[g] + m2d[g]; bIYes[g] = m2i[g] + m2e[g]; bDNo[g] = m2m[g]; bDYes[g] = m2d[g]; }
   ext[0] = sc[3]; ext[1] = sc[2]; ext[2] = sc[1]; ext[3] = sc[0];     // extendInsertNo=i2m, Yes=i2i, extendDeleteNo=d2m, Yes=d2d
+  return QG_OK;
+}
+
+// ---- overlap ---------------------------------------------------------------------------------------------------------
+extern "C" int qg_set_overlap_model (qg_ctx* ctx, const qg_overlap_model* m) {
+  if (!ctx || !m) return QG_ERR_INVALID;
+  if (m->match_k < 1 || m->match_k > 2 || m->gap_k < 0 || m->gap_k > 4)
+    QG_FAIL (ctx, QG_ERR_UNSUPPORTED, "overlap model orders K=%d G=%d: this build tabulates the pair emission for K <= 2 (the table grows as 16^K * 94^2 doubles)", m->match_k, m->gap_k);
+  qg_overlap_dev& d = ctx->omodel;
+  d.match_k = m->match_k; d.gap_k = m->gap_k; d.nK = qg_pow4 (m->match_k); d.nG = qg_pow4 (m->gap_k);
+  QG_TRY (qg_upload (ctx, d.d_match, m->match, sizeof (double) * 4 * d.nK * QG_NQ1));
+  QG_TRY (qg_upload (ctx, d.d_insert, m->insert, sizeof (double) * 4 * QG_NQ1));
+  for (int r = 0; r < 4; ++r) d.log_ref_base[r] = m->log_ref_base[r];
+  // transitions: qoverlap.cpp:22-48 (host arithmetic, once per model)
+  const uint64_t nG = d.nG;
+  std::vector<double> gapOpen (nG), m2m (nG * nG), m2i (nG * nG), m2d (nG * nG);
+  double sumP = 0, sumA = 0;
+  for (uint64_t j = 0; j < nG; ++j) {
+    const double readInsertProb = m->begin_insert[j];
+    const double readDeleteProb = (1 - m->begin_insert[j]) * m->begin_delete[j];
+    gapOpen[j] = readInsertProb + readDeleteProb;
+    const double pGapIsInsert = readInsertProb / gapOpen[j];
+    const double gapAdjacentProb = pGapIsInsert * readInsertProb + (1 - pGapIsInsert) * gapOpen[j] / (1 - m->extend_delete * (1 - gapOpen[j]));
+    sumP += pGapIsInsert; sumA += gapAdjacentProb;
+  }
+  for (uint64_t i = 0; i < nG; ++i)
+    for (uint64_t j = 0; j < nG; ++j) {
+      m2m[i * nG + j] = log (1 - gapOpen[i]) + log (1 - gapOpen[j]);
+      m2i[i * nG + j] = log (gapOpen[i]);
+      m2d[i * nG + j] = log (1 - gapOpen[i]) + log (gapOpen[j]);
+    }
+  const double pGapIsInsert = sumP / nG;
+  const double meanGapLength = pGapIsInsert / m->extend_insert + (1 - pGapIsInsert) / m->extend_delete;
+  const double gapExtendProb = 1 / meanGapLength;
+  const double gapAdjacentProb = sumA / nG;
+  d.i2i = d.d2d = log (gapExtendProb);
+  d.i2d = d.d2i = log (1 - gapExtendProb) + log (gapAdjacentProb);
+  d.i2m = d.d2m = log (1 - gapExtendProb) + log (1 - gapAdjacentProb);
+  QG_TRY (qg_upload (ctx, d.d_m2m, m2m.data (), sizeof (double) * nG * nG));
+  QG_TRY (qg_upload (ctx, d.d_m2i, m2i.data (), sizeof (double) * nG * nG));
+  QG_TRY (qg_upload (ctx, d.d_m2d, m2d.data (), sizeof (double) * nG * nG));
+  QG_CUDA (ctx, cudaStreamSynchronize (ctx->stream));
+  d.built[0] = d.built[1] = false;
+  d.set = true;
+  return QG_OK;
+}
+
+static int qg_overlap_ensure_table (qg_ctx* ctx, int strand, bool with_qual) {
+  qg_overlap_dev& d = ctx->omodel;
+  // d_none doubles as "table for this strand without qualities"; d_pair with
+  qg_dbuf& T = with_qual ? d.d_pair[strand] : d.d_none[strand];
+  const bool have = with_qual ? d.built[strand] : (d.d_none[strand].p != nullptr && d.d_xonly[strand].cap == 1);
+  if (have) return QG_OK;
+  const uint64_t nq = with_qual ? QG_NQUAL : 1;
+  const uint64_t total = d.nK * d.nK * nq * nq;
+  QG_TRY (qg_reserve (ctx, T, sizeof (double) * (total + 1)));
+  {
+    qg_timer tm (ctx, &ctx->stats.ms_prep);
+    QG_LAUNCH (qg_overlap_pair_table_kernel, (unsigned) ((total + 127) / 128), 128, 0, ctx->stream,
+               d.d_match.as<double> (), d.d_insert.as<double> (), ctx->d_lse.as<double> (),
+               d.log_ref_base[0], d.log_ref_base[1], d.log_ref_base[2], d.log_ref_base[3], d.match_k, strand, with_qual ? 1 : 0, T.as<double> ());
+    QG_TRY (qg_check_launch (ctx, "qg_overlap_pair_table_kernel"));
+  }
+  if (with_qual) d.built[strand] = true; else d.d_xonly[strand].cap = 1;   // marker only; d_xonly holds no memory
+  return QG_OK;
+}
+
+template<int DUMMY>
+static int qg_launch_overlap_fill (qg_ctx* ctx, const qg_dp_plan& plan, qg_ofill_args a, const qg_segment* d_segs_launch_order) {
+  for (const auto& L : plan.launches) {
+    a.segs = d_segs_launch_order + L.begin;
+    const bool multi = L.nw > 1;
+    const unsigned block = 32u * L.nw;
+#define QG_CASE(RR) case RR: \
+      if (multi) { auto kfn = qg_overlap_fill_kernel<8, true>; QG_LAUNCH (kfn, L.count, block, 0, ctx->stream, a); } \
+      else { auto kfn = qg_overlap_fill_kernel<RR, false>; QG_LAUNCH (kfn, L.count, block, 0, ctx->stream, a); } break;
+    switch (L.R) {
+      QG_CASE (2) QG_CASE (3) QG_CASE (4) QG_CASE (5) QG_CASE (6) QG_CASE (7) QG_CASE (8)
+      default: QG_FAIL (ctx, QG_ERR_INVALID, "internal: unsupported R=%d", L.R);
+    }
+#undef QG_CASE
+    QG_TRY (qg_check_launch (ctx, "qg_overlap_fill_kernel"));
+  }
+  return QG_OK;
+}
+
+extern "C" int qg_overlap_viterbi (qg_ctx* ctx, const qg_dpconfig* cfg, size_t n_pairs, const uint32_t* xi, const uint32_t* yi,
+                                   const uint8_t* y_complemented, const uint8_t* want_path,
+                                   double* score, uint32_t* coords4, uint8_t** path_out, uint64_t* path_offsets) {
+  if (!ctx || !cfg || !xi || !yi || !y_complemented || !score) return QG_ERR_INVALID;
+  if (!ctx->omodel.set) QG_FAIL (ctx, QG_ERR_STATE, "no overlap model: call qg_set_overlap_model first");
+  const qg_seqset& Y = ctx->seqs[QG_READS];
+  if (!Y.n) QG_FAIL (ctx, QG_ERR_STATE, "read set not uploaded");
+  const bool paths = path_out && path_offsets && coords4;
+  if (path_out) *path_out = nullptr;
+  const bool with_qual = Y.has_qual;
+  bool need[2] = {false, false};
+  for (size_t p = 0; p < n_pairs; ++p) need[y_complemented[p] ? 1 : 0] = true;
+  for (int s = 0; s < 2; ++s) if (need[s]) QG_TRY (qg_overlap_ensure_table (ctx, s, with_qual));
+  qg_overlap_dev& om = ctx->omodel;
+
+  qg_env_result er;
+  QG_TRY (qg_envelope_stage (ctx, cfg, 24, QG_READS, n_pairs, xi, yi, er));
+  size_t freeb = 0, totb = 0;
+  QG_CUDA (ctx, cudaMemGetInfo (&freeb, &totb));
+  const uint64_t budget = (uint64_t) qg_env_size ("QG_TRACE_BUDGET_MB", std::min<size_t> (freeb / 2, (size_t) 32 << 30) >> 20) << 20;
+  std::vector<uint8_t> all_paths;
+  std::vector<uint64_t> offs (n_pairs + 1, 0);
+  uint64_t path_total = 0;
+  size_t p0 = 0;
+  while (p0 < n_pairs) {
+    size_t p1 = p0; uint64_t words = 0;
+    while (p1 < n_pairs) {
+      uint64_t w = 0;
+      for (uint32_t r = er.run_begin[p1]; r < er.run_begin[p1 + 1]; ++r) {
+        int R, nw; const uint32_t width = (uint32_t) (er.runs[r].y - er.runs[r].x + 1);
+        if (qg_pick_R (width, &R, &nw) != QG_OK) QG_FAIL (ctx, QG_ERR_UNSUPPORTED, "pair %zu: a run of %u consecutive diagonals exceeds the %d this build fills with one CTA", p1, width, 256 * QG_MAX_NW);
+        w += ((uint64_t) Y.len (yi[p1]) + 32ull * nw + 1) * 32ull * nw;
+      }
+      if (p1 > p0 && (words + w) * 8 > budget) break;
+      words += w; ++p1;
+    }
+    const size_t np = p1 - p0;
+    qg_dp_plan plan;
+    QG_TRY (qg_build_plan (ctx, er, p0, p1, xi, yi, QG_READS, 3, plan));
+    for (uint32_t s : plan.order) plan.segs_sorted.push_back (plan.segs[s]);
+    std::vector<qg_opair> op (np);
+    uint64_t xa_tot = 0, yb_tot = 0, gx_tot = 0, gy_tot = 0, scratch_bytes = 0;
+    for (size_t p = 0; p < np; ++p) {
+      qg_opair& o = op[p];
+      o.xseq = xi[p0 + p]; o.yseq = yi[p0 + p]; o.xlen = Y.len (o.xseq); o.ylen = Y.len (o.yseq);
+      o.xoff = Y.off[o.xseq]; o.yoff = Y.off[o.yseq];
+      o.xa_off = xa_tot; xa_tot += o.xlen; o.yb_off = yb_tot; yb_tot += o.ylen;
+      o.gx_off = gx_tot; gx_tot += o.xlen + 1; o.gy_off = gy_tot; gy_tot += o.ylen + 1;
+      o.y_comp = y_complemented[p0 + p] ? 1 : 0; o.pad_ = 0;
+      plan.pairs[p].want_path = paths && (!want_path || want_path[p0 + p]) ? 1 : 0;
+      plan.pairs[p].path_off = scratch_bytes;
+      if (plan.pairs[p].want_path) scratch_bytes += plan.pairs[p].path_cap;
+    }
+    qg_dbuf &dOP = ctx->scratch[SC_RPJOBS], &dXA = ctx->scratch[SC_RP], &dYB = ctx->scratch[SC_STORE], &dGX = ctx->scratch[SC_ITEMRUNS], &dGY = ctx->scratch[SC_ITEMNRUNS];
+    qg_dbuf &dINS = ctx->scratch[SC_OUT1], &dLR = ctx->scratch[SC_ENDVALS], &dLC = ctx->scratch[SC_ROWACC];
+    {
+      qg_timer tm (ctx, &ctx->stats.ms_prep);
+      QG_TRY (qg_upload (ctx, dOP, op.data (), sizeof (qg_opair) * np));
+      QG_TRY (qg_reserve (ctx, dXA, sizeof (uint32_t) * (xa_tot + 1)));
+      QG_TRY (qg_reserve (ctx, dYB, sizeof (uint32_t) * (yb_tot + 1)));
+      QG_TRY (qg_reserve (ctx, dGX, sizeof (uint32_t) * (gx_tot + 1)));
+      QG_TRY (qg_reserve (ctx, dGY, sizeof (uint32_t) * (gy_tot + 1)));
+      QG_TRY (qg_reserve (ctx, dINS, sizeof (double) * 2 * (np + 1)));
+      QG_TRY (qg_reserve (ctx, dLR, sizeof (double) * (plan.aux_slots + 1)));
+      QG_TRY (qg_reserve (ctx, dLC, sizeof (double) * (plan.acc_rows + 1)));
+      QG_TRY (qg_upload (ctx, ctx->scratch[SC_SEGS], plan.segs_sorted.data (), sizeof (qg_segment) * plan.segs_sorted.size ()));
+      QG_TRY (qg_upload (ctx, ctx->scratch[SC_MISC0], plan.segs.data (), sizeof (qg_segment) * plan.segs.size ()));
+      QG_TRY (qg_upload (ctx, ctx->scratch[SC_PAIRDP], plan.pairs.data (), sizeof (qg_pair_dp) * np));
+      QG_TRY (qg_reserve (ctx, ctx->scratch[SC_TRACE], sizeof (unsigned long long) * (plan.trace_words + 1)));
+      QG_TRY (qg_reserve (ctx, ctx->scratch[SC_OUT0], sizeof (double) * (np + 1)));
+      QG_TRY (qg_reserve (ctx, ctx->scratch[SC_OUT2], sizeof (uint32_t) * 4 * (np + 1)));
+      QG_TRY (qg_reserve (ctx, ctx->scratch[SC_OUT3], sizeof (uint32_t) * (np + 1)));
+      QG_TRY (qg_reserve (ctx, ctx->scratch[SC_PATHSCR], scratch_bytes + 16));
+      QG_LAUNCH (qg_overlap_prep_kernel, (unsigned) np, 256, 0, ctx->stream,
+                 dOP.as<qg_opair> (), Y.d_tok.as<uint8_t> (), with_qual ? Y.d_qual.as<uint8_t> () : (const uint8_t*) nullptr,
+                 om.match_k, om.gap_k, with_qual ? 1 : 0, dXA.as<uint32_t> (), dYB.as<uint32_t> (), dGX.as<uint32_t> (), dGY.as<uint32_t> (),
+                 om.d_insert.as<double> (), dINS.as<double> ());
+      QG_TRY (qg_check_launch (ctx, "qg_overlap_prep_kernel"));
+      QG_LAUNCH (qg_fill_neginf_kernel, (unsigned) ((plan.acc_rows + 256) / 256), 256, 0, ctx->stream, dLC.as<double> (), plan.acc_rows + 1);
+      QG_TRY (qg_check_launch (ctx, "qg_fill_neginf_kernel"));
+    }
+    ctx->stats.trace_bytes += plan.trace_words * 8;
+    ctx->stats.n_segments += plan.segs.size ();
+    ctx->stats.cell_updates += qg_plan_cells (er, p0, p1);
+    {
+      qg_timer tm (ctx, &ctx->stats.ms_overlap);
+      qg_ofill_args a;
+      memset (&a, 0, sizeof (a));
+      a.pairs = dOP.as<qg_opair> ();
+      a.xa = dXA.as<uint32_t> (); a.yb = dYB.as<uint32_t> (); a.gx = dGX.as<uint32_t> (); a.gy = dGY.as<uint32_t> ();
+      a.table = with_qual ? om.d_pair[0].as<double> () : om.d_none[0].as<double> ();
+      a.table1 = with_qual ? om.d_pair[1].as<double> () : om.d_none[1].as<double> ();
+      a.m2m = om.d_m2m.as<double> (); a.m2i = om.d_m2i.as<double> (); a.m2d = om.d_m2d.as<double> ();
+      a.lse = ctx->d_lse.as<double> ();
+      // accessor swaps of qoverlap.h:46-51
+      a.effI2M = om.i2i; a.effI2I = om.i2m; a.effI2D = om.i2d; a.effD2M = om.d2i; a.effD2I = om.d2m; a.effD2D = om.d2d;
+      a.nG = (int) om.nG;
+      a.trace = (unsigned long long*) ctx->scratch[SC_TRACE].p;
+      a.lastrow = dLR.as<double> (); a.lastcol = dLC.as<double> ();
+      QG_TRY (qg_launch_overlap_fill<0> (ctx, plan, a, ctx->scratch[SC_SEGS].as<qg_segment> ()));
+    }
+    std::vector<uint32_t> plen (np), co (4 * np);
+    uint32_t flag = 0;
+    {
+      qg_timer tm (ctx, &ctx->stats.ms_traceback);
+      QG_CUDA (ctx, cudaMemsetAsync (ctx->scratch[SC_FLAGS].p, 0, 64, ctx->stream));
+      QG_LAUNCH (qg_overlap_traceback_kernel, (unsigned) ((np + 63) / 64), 64, 0, ctx->stream,
+                 ctx->scratch[SC_PAIRDP].as<qg_pair_dp> (), (uint32_t) np, ctx->scratch[SC_MISC0].as<qg_segment> (),
+                 dLR.as<double> (), dLC.as<double> (), dINS.as<double> (), (const unsigned long long*) ctx->scratch[SC_TRACE].p,
+                 ctx->scratch[SC_OUT0].as<double> (), ctx->scratch[SC_OUT2].as<uint32_t> (), ctx->scratch[SC_PATHSCR].as<uint8_t> (),
+                 ctx->scratch[SC_OUT3].as<uint32_t> (), (uint32_t*) ctx->scratch[SC_FLAGS].p);
+      QG_TRY (qg_check_launch (ctx, "qg_overlap_traceback_kernel"));
+    }
+    {
+      qg_timer tm (ctx, &ctx->stats.ms_d2h);
+      QG_TRY (qg_download (ctx, score + p0, ctx->scratch[SC_OUT0].p, sizeof (double) * np));
+      QG_TRY (qg_download (ctx, co.data (), ctx->scratch[SC_OUT2].p, sizeof (uint32_t) * 4 * np));
+      QG_TRY (qg_download (ctx, plen.data (), ctx->scratch[SC_OUT3].p, sizeof (uint32_t) * np));
+      QG_TRY (qg_download (ctx, &flag, ctx->scratch[SC_FLAGS].p, sizeof (uint32_t)));
+    }
+    if (flag) QG_FAIL (ctx, QG_ERR_CUDA, "internal: overlap traceback left the envelope (code %u)", flag);
+    if (coords4) memcpy (coords4 + 4 * p0, co.data (), sizeof (uint32_t) * 4 * np);
+    if (paths) {
+      std::vector<uint64_t> goff (np + 1, 0);
+      for (size_t p = 0; p < np; ++p) goff[p + 1] = goff[p] + plen[p];
+      for (size_t p = 0; p < np; ++p) offs[p0 + p] = path_total + goff[p];
+      if (goff[np]) {
+        qg_timer tm (ctx, &ctx->stats.ms_d2h);
+        QG_TRY (qg_upload (ctx, ctx->scratch[SC_MISC1], goff.data (), sizeof (uint64_t) * (np + 1)));
+        QG_TRY (qg_reserve (ctx, ctx->scratch[SC_PATHOUT], goff[np] + 16));
+        QG_LAUNCH (qg_path_gather_kernel, (unsigned) np, 128, 0, ctx->stream,
+                   ctx->scratch[SC_PAIRDP].as<qg_pair_dp> (), (uint32_t) np, ctx->scratch[SC_PATHSCR].as<uint8_t> (),
+                   ctx->scratch[SC_OUT3].as<uint32_t> (), ctx->scratch[SC_MISC1].as<uint64_t> (), ctx->scratch[SC_PATHOUT].as<uint8_t> ());
+        QG_TRY (qg_check_launch (ctx, "qg_path_gather_kernel"));
+        all_paths.resize (path_total + goff[np]);
+        QG_TRY (qg_download (ctx, all_paths.data () + path_total, ctx->scratch[SC_PATHOUT].p, goff[np]));
+      }
+      path_total += goff[np];
+    }
+    p0 = p1;
+  }
+  if (paths) {
+    offs[n_pairs] = path_total;
+    memcpy (path_offsets, offs.data (), sizeof (uint64_t) * (n_pairs + 1));
+    uint8_t* buf = (uint8_t*) malloc (path_total + 1);
+    if (!buf) QG_FAIL (ctx, QG_ERR_INVALID, "out of host memory");
+    if (path_total) memcpy (buf, all_paths.data (), path_total);
+    *path_out = buf;
+  }
+  return QG_OK;
+}
+
+// host string assembly, with the reference's squashing of adjacent insertions and deletions (qoverlap.cpp:231-267):
+// a gap run with deleted x bases X and inserted y bases Y becomes [X_t over Y_t for t < min] [rest of X over gaps] [gaps over rest of Y]
+extern "C" int qg_overlap_rows (const uint8_t* x_tok, const uint8_t* y_tok, const uint32_t* coords4,
+                                const uint8_t* path, uint64_t path_len, char** xrow, char** yrow) {
+  if (!x_tok || !y_tok || !coords4 || (!path && path_len) || !xrow || !yrow) return QG_ERR_INVALID;
+  static const char alph[] = "ACGT";
+  std::string xr, yr;
+  uint64_t i = coords4[0] ? coords4[0] - 1 : 0, j = coords4[2] ? coords4[2] - 1 : 0;
+  uint64_t t = 0;
+  while (t < path_len) {
+    if (path[t] == QG_OP_MATCH) { xr += alph[x_tok[i++] & 3]; yr += alph[y_tok[j++] & 3]; ++t; continue; }
+    uint64_t nd = 0, ni = 0, e = t;
+    while (e < path_len && path[e] != QG_OP_MATCH) { if (path[e] == QG_OP_DELETE) ++nd; else ++ni; ++e; }
+    const uint64_t sh = nd < ni ? nd : ni;
+    for (uint64_t s = 0; s < sh; ++s) { xr += alph[x_tok[i + s] & 3]; yr += alph[y_tok[j + s] & 3]; }
+    for (uint64_t s = sh; s < nd; ++s) { xr += alph[x_tok[i + s] & 3]; yr += '-'; }
+    for (uint64_t s = sh; s < ni; ++s) { xr += '-'; yr += alph[y_tok[j + s] & 3]; }
+    i += nd; j += ni; t = e;
+  }
+  *xrow = (char*) malloc (xr.size () + 1); *yrow = (char*) malloc (yr.size () + 1);
+  if (!*xrow || !*yrow) return QG_ERR_INVALID;
+  memcpy (*xrow, xr.c_str (), xr.size () + 1); memcpy (*yrow, yr.c_str (), yr.size () + 1);
+  return QG_OK;
+}
+
+// ---- seam B: QuaffOverlapAligner::align (qoverlap.cpp:312-334); pair order of QuaffOverlapScheduler (qoverlap.cpp:473-478, 528-547)
+extern "C" int qg_overlap_reads (qg_ctx* ctx, const qg_dpconfig* cfg, size_t n_originals, const double* null_loglike,
+                                 size_t* n_pairs_out, uint32_t** xi_out, uint32_t** yi_out,
+                                 double** score_out, uint32_t** coords4_out, uint8_t** path_out, uint64_t** path_offsets_out) {
+  if (!ctx || !cfg || !null_loglike || !n_pairs_out || !xi_out || !yi_out || !score_out || !coords4_out || !path_out || !path_offsets_out) return QG_ERR_INVALID;
+  const size_t N = ctx->seqs[QG_READS].n;
+  if (n_originals > N) QG_FAIL (ctx, QG_ERR_INVALID, "n_originals exceeds the read set");
+  std::vector<uint32_t> xi, yi; std::vector<uint8_t> yc;
+  for (size_t nx = 0; nx + 1 < n_originals; ++nx)
+    for (size_t ny = nx + 1; ny < N; ++ny) { xi.push_back ((uint32_t) nx); yi.push_back ((uint32_t) ny); yc.push_back (ny >= n_originals ? 1 : 0); }
+  const size_t np = xi.size ();
+  double* sc = (double*) malloc (sizeof (double) * (np + 1));
+  uint32_t* co = (uint32_t*) malloc (sizeof (uint32_t) * 4 * (np + 1));
+  uint64_t* po = (uint64_t*) malloc (sizeof (uint64_t) * (np + 2));
+  uint32_t* xo = (uint32_t*) malloc (sizeof (uint32_t) * (np + 1));
+  uint32_t* yo = (uint32_t*) malloc (sizeof (uint32_t) * (np + 1));
+  if (!sc || !co || !po || !xo || !yo) QG_FAIL (ctx, QG_ERR_INVALID, "out of host memory");
+  uint8_t* paths = nullptr;
+  po[0] = 0;
+  if (np) {
+    const int rc = qg_overlap_viterbi (ctx, cfg, np, xi.data (), yi.data (), yc.data (), nullptr, sc, co, &paths, po);
+    if (rc != QG_OK) { free (sc); free (co); free (po); free (xo); free (yo); return rc; }
+    // scoreAdjustedAlignment (qoverlap.cpp:292-302): minus the null log-likelihood of x and of y as stored
+    for (size_t p = 0; p < np; ++p) { if (sc[p] > -INFINITY) { sc[p] -= null_loglike[xi[p]]; sc[p] -= null_loglike[yi[p]]; } xo[p] = xi[p]; yo[p] = yi[p]; }
+  } else paths = (uint8_t*) malloc (1);
+  *n_pairs_out = np; *xi_out = xo; *yi_out = yo; *score_out = sc; *coords4_out = co; *path_out = paths; *path_offsets_out = po;
   return QG_OK;
 }

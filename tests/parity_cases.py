@@ -112,3 +112,31 @@ def check_estep(G, O, x, reads, s_or, nullp, cfg, use_null=True, n_iter=2, rel=1
         assert abs(g["loglike"] - o["loglike"].sum()) <= 1e-9 * abs(g["loglike"])
         so_g, so_o = g["sort_order"], o["sort_order"]
     return g
+
+
+def overlap_pairs(n_originals, n_total):
+    """QuaffOverlapScheduler order (qoverlap.cpp:473-478, 528-547)."""
+    xi, yi, yc = [], [], []
+    for nx in range(max(n_originals - 1, 0)):
+        for ny in range(nx + 1, n_total):
+            xi.append(nx); yi.append(ny); yc.append(1 if ny >= n_originals else 0)
+    return np.array(xi, np.uint32), np.array(yi, np.uint32), np.array(yc, np.uint8)
+
+
+def check_overlap(G, O, seqs, n_originals, qp, cfg, use_quals=True):
+    """bit-exact: result, end coordinates and both gapped rows (after the reference's indel squashing)"""
+    bufs = [po.SeqBuf(s.tokens(), s.qual_scores() if use_quals else None) for s in seqs]
+    os_ = [O.overlap_scores(qp, False), O.overlap_scores(qp, True)]
+    xi, yi, yc = overlap_pairs(n_originals, len(seqs))
+    r = G.overlap_viterbi(cfg, xi, yi, yc)
+    oc = oracle_cfg(cfg)
+    n_finite = 0
+    for p in range(len(xi)):
+        o = O.overlap_viterbi(bufs[xi[p]], bufs[yi[p]], os_[yc[p]], oc)
+        assert o["result"] == r["score"][p] or (np.isinf(o["result"]) and np.isinf(r["score"][p])), (p, o["result"], r["score"][p])
+        if np.isfinite(o["result"]):
+            n_finite += 1
+            assert tuple(int(v) for v in r["coords"][p]) == tuple(o["coords"]), (p, r["coords"][p], o["coords"])
+            xr, yr = G.overlap_rows(bufs[xi[p]].tok, bufs[yi[p]].tok, r["coords"][p], r["paths"][p])
+            assert xr == o["xrow"] and yr == o["yrow"], f"pair {p}: rows differ"
+    return r, n_finite

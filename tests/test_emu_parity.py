@@ -63,3 +63,24 @@ def test_emu_align_reads_and_estep(emu, oracle, workload):
         assert a["score"][m] == bo["result"] - null_ll[m]
         assert a["x_start"][m] == bo["x_start"] and a["x_end"][m] == bo["x_end"]
         assert np.array_equal(a["paths"][m], bo["path"])
+
+
+def test_emu_memory_guided_envelopes(emu, oracle, workload):
+    """-kmatchmb: tiers accepted while the storage diagonals fit (diagenv.cpp:62-96, kmerThreshold < 0)"""
+    x, reads, _ = workload
+    xi, yi = pc.all_pairs(len(x), len(reads))
+    for mb_bytes, cell in ((1 << 20, 24), (300_000, 24), (3_000_000, 48), (50_000, 24), (1 << 30, 24)):
+        cfg = api.dp_config(kmer_threshold=-1, max_size=mb_bytes)
+        pc.check_envelopes(emu, oracle, x, reads, cfg, xi, yi, cell_size=cell)
+
+
+def test_emu_overlap(emu, oracle):
+    from quaff_b200.synth import random_ref, sample_reads
+    from quaff_b200.seqs import add_revcomps
+    ref = random_ref(420, 21)
+    reads, _, _ = sample_reads(ref, 3, 260, 22, both_strands=True)
+    seqs = add_revcomps(reads)
+    qp = pc.default_params()
+    emu.set_reads(seqs); emu.set_overlap_params(qp)
+    r, nf = pc.check_overlap(emu, oracle, seqs, len(reads), qp, api.dp_config(kmer_threshold=5))
+    assert nf > 0

@@ -49,3 +49,75 @@ def test_full_dp_small(gpu, oracle):
     pc.check_envelopes(gpu, oracle, x, reads, cfg, xi, yi)
     pc.check_viterbi(gpu, oracle, x, reads, s_or, cfg, xi, yi)
     pc.check_forward(gpu, oracle, x, reads, s_or, cfg, xi, yi)
+
+
+def test_backward_counts(gpu, oracle, workload):
+    x, reads, s_or = workload
+    xi, yi = pc.all_pairs(len(x), len(reads))
+    pc.check_backward(gpu, oracle, x, reads, s_or, api.dp_config(kmer_threshold=20), xi, yi)
+
+
+def test_estep_and_align_reads(gpu, oracle, workload):
+    import os
+    from quaff_b200.params import QuaffNullParams
+    x, reads, s_or = workload
+    nullp = QuaffNullParams.load(os.path.join(os.path.dirname(__file__), "golden", "testquaffnullparams.json"))
+    cfg = api.dp_config(kmer_threshold=20)
+    pc.check_estep(gpu, oracle, x, reads, s_or, nullp, cfg, use_null=True, n_iter=2)
+    pc.check_estep(gpu, oracle, x, reads, s_or, nullp, cfg, use_null=False, n_iter=1)
+    null_ll = np.array([api.null_loglike(nullp, r, gpu.L) for r in reads])
+    a = gpu.align_reads(cfg, null_ll)
+    xs, ys = pc.seqbufs(x, reads)
+    for m in range(len(reads)):
+        best, bo = None, None
+        for n in range(len(x)):
+            o = oracle.viterbi(xs[n], ys[m], s_or, pc.oracle_cfg(cfg))
+            if np.isfinite(o["result"]) and (bo is None or o["result"] > bo["result"]):
+                best, bo = n, o
+        assert a["best_ref"][m] == best and a["score"][m] == bo["result"] - null_ll[m]
+        assert a["x_start"][m] == bo["x_start"] and a["x_end"][m] == bo["x_end"] and np.array_equal(a["paths"][m], bo["path"])
+
+
+def test_memory_guided_envelopes(gpu, oracle, workload):
+    x, reads, _ = workload
+    xi, yi = pc.all_pairs(len(x), len(reads))
+    for nbytes, cell in ((10 << 20, 24), (2_000_000, 24), (20_000_000, 48), (400_000, 24)):
+        pc.check_envelopes(gpu, oracle, x, reads, api.dp_config(kmer_threshold=-1, max_size=nbytes), xi, yi, cell_size=cell)
+
+
+def test_order2_params(gpu, oracle):
+    """-order 2: k-mer context for substitutions (K = 3) and gap opening (G = 2)"""
+    from quaff_b200.params import random_params
+    x, reads = pc.make_workload(ref_len=20000, n_reads=3, read_len=1500, seed=7)
+    qp = random_params(np.random.default_rng(5), match_k=3, gap_k=2)
+    gpu.set_refs(x); gpu.set_reads(reads); gpu.set_params(qp)
+    s_or = oracle.scores(qp)
+    xi, yi = pc.all_pairs(len(x), len(reads))
+    cfg = api.dp_config(kmer_threshold=14)
+    pc.check_viterbi(gpu, oracle, x, reads, s_or, cfg, xi, yi)
+    pc.check_forward(gpu, oracle, x, reads, s_or, cfg, xi, yi)
+    pc.check_backward(gpu, oracle, x, reads, s_or, cfg, xi, yi)
+
+
+def test_noquals(gpu, oracle):
+    x, reads = pc.make_workload(ref_len=20000, n_reads=3, read_len=1200, seed=9)
+    qp = pc.default_params()
+    gpu.set_refs(x); gpu.set_reads(reads, use_quals=False); gpu.set_params(qp)
+    s_or = oracle.scores(qp)
+    xi, yi = pc.all_pairs(len(x), len(reads))
+    cfg = api.dp_config(kmer_threshold=14)
+    pc.check_viterbi(gpu, oracle, x, reads, s_or, cfg, xi, yi, use_quals=False)
+    pc.check_forward(gpu, oracle, x, reads, s_or, cfg, xi, yi, use_quals=False)
+
+
+def test_overlap(gpu, oracle):
+    from quaff_b200.synth import random_ref, sample_reads
+    from quaff_b200.seqs import add_revcomps
+    ref = random_ref(4000, 21)
+    reads, _, _ = sample_reads(ref, 5, 2200, 22, both_strands=True)
+    seqs = add_revcomps(reads)
+    qp = pc.default_params()
+    gpu.set_reads(seqs); gpu.set_overlap_params(qp)
+    r, nf = pc.check_overlap(gpu, oracle, seqs, len(reads), qp, api.dp_config(kmer_threshold=14))
+    assert nf >= 5
+    r, nf = pc.check_overlap(gpu, oracle, seqs, len(reads), qp, api.dp_config(kmer_threshold=14), use_quals=True)
