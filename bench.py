@@ -1,0 +1,365 @@
+#!/usr/bin/env python
+"""bench.py -- the headline benchmark of BASELINE.json: `quaff align -kmatchband 64` on synthetic nanopore-like
+8 kb reads against a 5 Mb reference, both strands (config 4), sharded by read over N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+A step = one batch of READS_PER_STEP reads per GPU through the whole hot path: k-mer seeding -> diagonal
+envelope -> banded Viterbi fill -> best strand -> traceback -> paths on the host.
+  value : reads/s of the whole job with the step's reads already resident in HBM (timed between
+          torch.cuda.synchronize + barrier, max over ranks)
+  e2e   : the same through the reference-facing call with HOST buffers: upload of the step's reads and download of
+          the scores/paths inside the timed region
+`--impl reference` times the reference's own CPU implementation (oracle/_ref/quaff, the unmodified sources built -O3,
+`-threads <all host cores>`) on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+REF_LEN = 5_000_000
+READ_LEN = 8000
+READS_PER_STEP = 1536            # per GPU; ~4.3 GB of traceback pointers per step
+POOL_BATCHES = 2                 # distinct read batches cycled through the steps (bounds host synthesis time)
+# peak lane-instructions/s and the instructions one cell update needs in the minimal formulation
+SM_COUNT, LANES, SM_MAX_MHZ = 148, 128, 1965.0
+PEAK_LANE_INSTR = SM_COUNT * LANES * SM_MAX_MHZ * 1e6
+INSTR_PER_CU = dict(viterbi=13, forward=9, backward=25, overlap=26)
+PEAK_SMEM_ATOMIC = SM_COUNT * 32 * SM_MAX_MHZ * 1e6      # histogram increments/s upper bound
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as fh:
+            d = json.load(fh)
+        return float(d.get("hbm_gbs", 6650.0)), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index: int):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}",
+                 "--query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+                 "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap",
+                 "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_workload(rank: int, n_batches: int, reads_per_step: int, ref_len: int = REF_LEN, read_len: int = READ_LEN):
+    from quaff_b200.seqs import add_revcomps
+    from quaff_b200.synth import random_ref, sample_reads
+    ref = random_ref(ref_len, 1)                                   # reference seed 1, read seed 2 (+ rank)
+    batches = []
+    for b in range(n_batches):
+        reads, _, _ = sample_reads(ref, reads_per_step, read_len, 2 + 1000 * rank + b, name_prefix=f"r{rank}b{b}_")
+        batches.append(reads)
+    return add_revcomps([ref]), batches
+
+
+def load_models():
+    from quaff_b200.params import QuaffNullParams, QuaffParams
+    qp = QuaffParams.load(os.path.join(ROOT, "tests", "golden", "defaultparams.json"))
+    nullp = QuaffNullParams.load(os.path.join(ROOT, "tests", "golden", "testquaffnullparams.json"))
+    return qp, nullp
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def reference_cpu_run(n_reads: int, threads: int, ref_len: int = REF_LEN, read_len: int = READ_LEN, seed_rank: int = 0):
+    """`quaff align ref.fa reads.fq -kmatchband 64 -threads T` with the reference binary built from the unmodified
+    sources (oracle/_ref/quaff).  Returns (reads/s, seconds, kind)."""
+    from oracle import pyoracle as po
+    from quaff_b200.synth import random_ref, sample_reads
+    qp, nullp = load_models()
+    ref = random_ref(ref_len, 1)
+    reads, _, _ = sample_reads(ref, n_reads, read_len, 2 + 1000 * seed_rank, name_prefix="r")
+    if os.path.exists(po.REF_QUAFF):
+        with tempfile.TemporaryDirectory() as td:
+            fa, fq = os.path.join(td, "ref.fa"), os.path.join(td, "reads.fq")
+            pj, nj = os.path.join(td, "params.json"), os.path.join(td, "null.json")
+            with open(fa, "w") as fh:
+                fh.write(f">{ref.name}\n{ref.seq}\n")
+            with open(fq, "w") as fh:
+                for r in reads:
+                    fh.write(f"@{r.name}\n{r.seq}\n+\n{r.qual}\n")
+            open(pj, "w").write(qp.to_json()); open(nj, "w").write(nullp.to_json())
+            cmd = [po.REF_QUAFF, "align", fa, fq, "-params", pj, "-null", nj, "-kmatchband", "64", "-format", "sam", "-threads", str(threads)]
+            t0 = time.time()
+            res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+            dt = time.time() - t0
+            if res.returncode != 0:
+                raise RuntimeError("reference quaff failed: " + res.stderr[-500:])
+            n_out = sum(1 for ln in res.stdout.splitlines() if ln and not ln.startswith("@"))
+        return n_reads / dt, dt, "reference", n_out
+    # no reference build here: time the C restatement (1 thread)
+    O = po.Oracle()
+    s = O.scores(qp)
+    from quaff_b200.seqs import add_revcomps
+    xs = [po.SeqBuf(v.tokens(), None) for v in add_revcomps([ref])]
+    cfg = po.make_config(kmer_threshold=20)
+    t0 = time.time()
+    for r in reads:
+        y = po.SeqBuf(r.tokens(), r.qual_scores())
+        for x in xs:
+            O.viterbi(x, y, s, cfg)
+    dt = time.time() - t0
+    return n_reads / dt, dt, "port", n_reads
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    sample = max(2, min(cores, 32))                               # about one read per core: 13 s/read/core at this shape
+    vals = []
+    for _ in range(args.warmup + args.steps if args.ref_all_steps else 1):
+        v, dt, kind, _ = reference_cpu_run(sample, cores)
+        vals.append((v, dt))
+    v = float(np.mean([a for a, _ in vals])); dt = float(np.mean([b for _, b in vals]))
+    line = {
+        "impl": "reference", "metric": "align_reads_per_sec", "value": v, "unit": "reads/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "cfg4: quaff align, 8 kb reads vs 5 Mb reference, both strands, -kmatch 6 -kmatchn 20 -kmatchband 64",
+                   "reads_per_step": sample, "note": "bounded sample of the same workload; reference CPU implementation, all host threads"},
+        "cpu_baseline": {"value": v, "unit": "reads/s", "cores": cores, "kind": kind, "sample": f"{sample} reads x 8 kb vs 5 Mb, both strands, -threads {cores}"},
+        "e2e": {"value": v, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="quaff_b200")
+    ap.add_argument("--reads-per-step", type=int, default=READS_PER_STEP)
+    ap.add_argument("--ref-len", type=int, default=REF_LEN)
+    ap.add_argument("--read-len", type=int, default=READ_LEN)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the Forward/Backward side measurement")
+    ap.add_argument("--ref-all-steps", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl != "reference":
+        args.warmup = max(args.warmup, 3) if os.environ.get("QB_ALLOW_SHORT_WARMUP") is None else args.warmup
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from quaff_b200 import api
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device: there is no CPU path"
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    B = args.reads_per_step
+    x, batches = make_workload(rank, POOL_BATCHES, B, args.ref_len, args.read_len)
+    qp, nullp = load_models()
+    G = api.QuaffGPU(device=local)
+    G.set_refs(x); G.set_params(qp)
+    cfg = api.dp_config(kmer_threshold=20, band_size=64, kmer_len=6)
+    flat = [api._flatten(b, True) for b in batches]
+    null_ll = [np.array([api.null_loglike(nullp, r, G.L) for r in b]) for b in batches]
+    # pinned host staging for the e2e arm
+    pinned = []
+    for tok, qual, off in flat:
+        pt = torch.from_numpy(tok).pin_memory(); pq = torch.from_numpy(qual).pin_memory()
+        pinned.append((pt.numpy(), pq.numpy(), off))
+
+    # ---- resident-input arm: all pool batches live on the device as one READS set --------------------------------
+    all_reads = [r for b in batches for r in b]
+    G.set_reads(all_reads)
+    all_null = np.concatenate(null_ll)
+
+    def resident_step(i):
+        b = i % POOL_BATCHES
+        return G.align_reads(cfg, all_null[b * B:(b + 1) * B], first=b * B, count=B, split_paths=False)
+
+    for i in range(args.warmup):
+        resident_step(i)
+    sampler = ClockSampler(local); sampler.start()
+    G.stats(reset=True)
+    barrier(); t0 = time.perf_counter()
+    for i in range(args.steps):
+        out = resident_step(args.warmup + i)
+    barrier(); t1 = time.perf_counter()
+    st = G.stats()
+    dt = t1 - t0
+    # ---- e2e arm: host buffers in, host results out, every step ---------------------------------------------------
+    def e2e_step(i):
+        b = i % POOL_BATCHES
+        tok, qual, off = pinned[b]
+        G.set_seqs_raw(api.QG_READS, tok, qual, off)
+        r = G.align_reads(cfg, null_ll[b], split_paths=False)
+        return r
+
+    for i in range(args.warmup):
+        e2e_step(i)
+    G.stats(reset=True)
+    barrier(); t2 = time.perf_counter()
+    for i in range(args.steps):
+        r = e2e_step(args.warmup + i)
+    barrier(); t3 = time.perf_counter()
+    st_e = G.stats()
+    clocks = sampler.stop()
+    dt_e = t3 - t2
+    h2d = int(pinned[0][0].nbytes + pinned[0][1].nbytes + pinned[0][2].nbytes)
+    d2h = int(r["paths"].nbytes + r["score"].nbytes + r["best_ref"].nbytes + r["x_start"].nbytes + r["x_end"].nbytes + r["path_offsets"].nbytes)
+
+    # ---- side measurement: Forward / Backward (train) GCUPS on a slice of the same reads ---------------------------
+    train = None
+    if not args.no_train:
+        nt = min(B, 192)
+        G.set_reads(batches[0][:nt])
+        xi = np.tile(np.arange(2, dtype=np.uint32), nt); yi = np.repeat(np.arange(nt, dtype=np.uint32), 2)
+        G.forward(cfg, xi, yi)
+        G.stats(reset=True)
+        G.forward(cfg, xi, yi)
+        s1 = G.stats(reset=True)
+        sel = xi == xi                                               # Backward for every pair of the slice
+        G.backward_counts(cfg, xi[sel], yi[sel])
+        s2 = G.stats(reset=True)
+        cu_f = s1["cell_updates"]; cu_b = s2["cell_updates"] / 2
+        train = {"pairs": int(len(xi)), "forward_gcups": cu_f / 1e9 / (s1["ms_forward"] / 1e3),
+                 "backward_gcups": cu_b / 1e9 / (s2["ms_backward"] / 1e3),
+                 "fwd_bwd_gcups": 2 * cu_b / 1e9 / ((s2["ms_forward"] + s2["ms_backward"]) / 1e3),
+                 "formulation": "FP64 log space, the reference's table log-sum-exp (bit-exact Forward)"}
+
+    # ---- reduce over ranks: the slowest rank defines the step -----------------------------------------------------
+    times = torch.tensor([dt, dt_e], dtype=torch.float64, device="cuda")
+    sums = torch.tensor([float(st["cell_updates"]), float(st["kmer_hits"]), st["ms_seed"], st["ms_viterbi"], st["ms_traceback"],
+                         float(st["kernel_launches"]), float(st["trace_bytes"])], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+        stage_max = sums.clone(); dist.all_reduce(stage_max, op=dist.ReduceOp.MAX)
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+    else:
+        stage_max = sums
+    dt, dt_e = float(times[0]), float(times[1])
+    total_reads = B * args.steps * world
+    value = total_reads / dt
+    e2e_value = total_reads / dt_e
+
+    if rank == 0:
+        cu_total, hits_total = float(sums[0]), float(sums[1])
+        ms_seed, ms_vit, ms_tb = float(stage_max[2]), float(stage_max[3]), float(stage_max[4])
+        launches = int(float(sums[5]) / world)
+        hbm_peak, peak_src = measured_peaks()
+        cu_rank = cu_total / world; hits_rank = hits_total / world
+        vit_cups = cu_rank / (ms_vit / 1e3); seed_hps = hits_rank / (ms_seed / 1e3)
+        # dominant kernel by device time
+        seed_dom = ms_seed >= ms_vit
+        # algorithmic HBM bytes: seeding streams the 2 B/position k-mer codes of the reference once per (read, strand,
+        # chunk overlap) ; the Viterbi fill writes 4 B of pointers per lane and macro-step (= trace_bytes)
+        seed_bytes = 2.0 * (args.ref_len * 2) * B * args.steps
+        vit_bytes = float(sums[6]) / world
+        roofline = {
+            "kernel": "qg_seed_kernel" if seed_dom else "qg_fill_kernel<R,Viterbi>",
+            "bound": "smem_atomic" if seed_dom else "fp64_issue",
+            "achieved": seed_hps / 1e9 if seed_dom else vit_cups / 1e9,
+            "peak": PEAK_SMEM_ATOMIC / 1e9 if seed_dom else PEAK_LANE_INSTR / INSTR_PER_CU["viterbi"] / 1e9,
+            "unit": "Ghit/s" if seed_dom else "GCUPS",
+            "frac": (seed_hps / PEAK_SMEM_ATOMIC) if seed_dom else vit_cups / (PEAK_LANE_INSTR / INSTR_PER_CU["viterbi"]),
+            "traffic": None,
+            "definition": "SURVEY.md 8d / DESIGN.md: neither kernel is HBM- or tensor-bound; peaks are the shared-memory atomic issue "
+                          "rate (148 SM x 32 lanes x 1965 MHz) and 148 x 128 x 1965 MHz lane-instructions/s over 13 instr per cell update",
+            "hbm": {"seed_GBps": seed_bytes / (ms_seed / 1e3) / 1e9, "viterbi_trace_GBps": vit_bytes / (ms_vit / 1e3) / 1e9,
+                    "peak_GBps": hbm_peak, "peak_source": peak_src},
+            "all": {"seed_ghits_s": seed_hps / 1e9, "seed_frac_of_smem_atomic_peak": seed_hps / PEAK_SMEM_ATOMIC,
+                    "viterbi_gcups": vit_cups / 1e9, "viterbi_frac_of_fp32_roofline": vit_cups / (PEAK_LANE_INSTR / INSTR_PER_CU["viterbi"]),
+                    "viterbi_frac_of_fp64_roofline": vit_cups / (PEAK_LANE_INSTR / 2 / INSTR_PER_CU["viterbi"]),
+                    "ms_per_step": {"seed": ms_seed / args.steps, "viterbi_fill": ms_vit / args.steps, "traceback": ms_tb / args.steps}},
+        }
+        if train:
+            roofline["all"]["forward_gcups"] = train["forward_gcups"]; roofline["all"]["backward_gcups"] = train["backward_gcups"]
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            sample = max(2, min(cores, 32))
+            try:
+                v, secs, kind, _ = reference_cpu_run(sample, cores, args.ref_len, args.read_len)
+                cpu = {"value": v, "unit": "reads/s", "cores": cores, "kind": kind,
+                       "sample": f"{sample} reads x {args.read_len} b vs {args.ref_len} b, both strands, quaff align -threads {cores} ({secs:.1f} s)"}
+            except Exception as e:                                    # the baseline is reported, never required
+                cpu = {"value": None, "unit": "reads/s", "cores": cores, "kind": "unavailable", "sample": str(e)[:200]}
+        line = {
+            "metric": "align_reads_per_sec", "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "cfg4: quaff align, synthetic 8 kb nanopore-like reads (12% error) vs 5 Mb random reference, both strands, "
+                                   "-kmatch 6 -kmatchn 20 -kmatchband 64, default params, fixed null model",
+                       "reads_per_step_per_gpu": B, "ref_len": args.ref_len, "read_len": args.read_len,
+                       "sharding": "reads over ranks, reference replicated, no collective on the align path",
+                       "l2": "inputs larger than L2: every step writes and re-reads its own ~%.1f GB of traceback pointers and alternates between %d read batches"
+                             % (float(sums[6]) / world / args.steps / 1e9, POOL_BATCHES)},
+            "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": dt_e / args.steps * 1e3},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "gcups": {"viterbi_fill": vit_cups / 1e9, "cell_updates_per_read": cu_rank / (B * args.steps), "kmer_hits_per_read": hits_rank / (B * args.steps)},
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "train": train,
+        }
+        print(json.dumps(line), flush=True)
+    G.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -147,6 +147,12 @@ int qg_align_reads (qg_ctx* ctx, const qg_dpconfig* cfg, const double* null_logl
                     uint32_t* best_ref, double* score, uint32_t* x_start, uint32_t* x_end,
                     uint8_t** path_out, uint64_t* path_offsets /* n_reads+1 */);
 
+/* the same over reads [first_read, first_read + n_reads) of the READS set (outputs sized n_reads): lets a caller that
+ * keeps a large read set resident on the device drive it batch by batch                               */
+int qg_align_reads_range (qg_ctx* ctx, const qg_dpconfig* cfg, size_t first_read, size_t n_reads, const double* null_loglike,
+                          uint32_t* best_ref, double* score, uint32_t* x_start, uint32_t* x_end,
+                          uint8_t** path_out, uint64_t* path_offsets /* n_reads+1 */);
+
 /* ---- seam C: QuaffTrainer::getCounts (qmodel.cpp:2005), one E-step over this rank's reads --------- */
 /* sort_order: in/out [n_reads][n_refs] with lengths sort_len[n_reads] (qmodel.cpp:2247, 2264-2270);
  * null_loglike[n_reads] used when use_null.  y_loglike[n_reads]; param_counts (QuaffParamCounts layout)

@@ -348,6 +348,12 @@ class Ref:
                 d.p, d.q, d.r = map(float, mat[3*(i*nK+j):3*(i*nK+j)+3])
         return out
 
+    def null_fit(self, hseqs):
+        """QuaffNullParams fitted from reads, as `quaff align/overlap/count` do without -null"""
+        arr = (C.c_void_p * len(hseqs))(*hseqs)
+        self.L.qref_null_fit.restype = C.c_void_p
+        return self.L.qref_null_fit(arr, len(hseqs))
+
     def null_as_parsed(self, hn, np_):
         import copy
         out = copy.deepcopy(np_)

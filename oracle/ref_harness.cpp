@@ -152,6 +152,15 @@ int qref_null_values (void* p, double* nullEmit, double* nullPQR) {
   return 0;
 }
 
+
+// QuaffNullParams (const vguard<FastSeq>&, double) -- the null model auto-fitted from the reads when -null is
+// absent (qmodel.cpp:1811-1843; t/quaff.cpp:419-424); returned through qref_null_values
+void* qref_null_fit (void** seqs, int n) {
+  vguard<FastSeq> v;
+  for (int i = 0; i < n; ++i) v.push_back (*(const FastSeq*) seqs[i]);
+  return new QuaffNullParams (v);
+}
+
 // QuaffNullParams::readJson (qmodel.cpp:1845-1848)
 void* qref_null_from_json (const char* text) {
   QuaffNullParams* np = new QuaffNullParams();

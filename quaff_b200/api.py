@@ -32,7 +32,7 @@ c_u64_p = C.POINTER(C.c_uint64)
 ABI_SYMBOLS = [
     "qg_counts_size", "qg_create", "qg_destroy", "qg_last_error", "qg_free", "qg_abi_version", "qg_set_seqs",
     "qg_set_align_model", "qg_scores_from_params", "qg_null_loglike", "qg_envelopes", "qg_viterbi", "qg_forward",
-    "qg_backward_counts", "qg_align_reads", "qg_estep", "qg_set_overlap_model", "qg_overlap_viterbi", "qg_overlap_rows",
+    "qg_backward_counts", "qg_align_reads", "qg_align_reads_range", "qg_estep", "qg_set_overlap_model", "qg_overlap_viterbi", "qg_overlap_rows",
     "qg_overlap_reads", "qg_get_stats",
 ]
 
@@ -267,14 +267,24 @@ class QuaffGPU:
         return dict(fwd=f, back=b, counts=csum, counts_per_pair=cpp)
 
     # ---- seam A: QuaffAligner::align (qmodel.cpp:2624) -----------------------------------------------
-    def align_reads(self, cfg: DPConfig, null_ll: np.ndarray):
-        n = self.n[QG_READS]
+    def align_reads(self, cfg: DPConfig, null_ll: np.ndarray, first: int = 0, count: Optional[int] = None, split_paths: bool = True):
+        """best reference per read of READS[first : first + count] (default: the whole set)"""
+        n = self.n[QG_READS] - first if count is None else int(count)
         null_ll = np.ascontiguousarray(null_ll, dtype=np.float64)
+        assert len(null_ll) == n
         best = np.zeros(n, np.uint32); score = np.zeros(n); xs = np.zeros(n, np.uint32); xe = np.zeros(n, np.uint32)
         path = c_u8_p(); off = np.zeros(n + 1, dtype=np.uint64)
-        self._check(self.L.qg_align_reads(self.ctx, C.byref(cfg), _dp(null_ll), best.ctypes.data_as(c_u32_p), _dp(score),
-                                          xs.ctypes.data_as(c_u32_p), xe.ctypes.data_as(c_u32_p), C.byref(path), off.ctypes.data_as(c_u64_p)))
-        return dict(best_ref=best, score=score, x_start=xs, x_end=xe, paths=self._take_paths(path, off, n))
+        self._check(self.L.qg_align_reads_range(self.ctx, C.byref(cfg), C.c_size_t(first), C.c_size_t(n), _dp(null_ll),
+                                                best.ctypes.data_as(c_u32_p), _dp(score), xs.ctypes.data_as(c_u32_p),
+                                                xe.ctypes.data_as(c_u32_p), C.byref(path), off.ctypes.data_as(c_u64_p)))
+        if split_paths:
+            paths = self._take_paths(path, off, n)
+        else:
+            total = int(off[n])
+            paths = np.ctypeslib.as_array(path, shape=(max(total, 1),))[:total].copy() if path else np.zeros(0, np.uint8)
+            if path:
+                self.L.qg_free(path)
+        return dict(best_ref=best, score=score, x_start=xs, x_end=xe, paths=paths, path_offsets=off)
 
     # ---- seam C: QuaffTrainer::getCounts (qmodel.cpp:2005) --------------------------------------------
     def estep(self, cfg: DPConfig, use_null: bool, null_ll: np.ndarray, sort_order: Optional[List[List[int]]] = None):

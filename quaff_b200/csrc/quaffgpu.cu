@@ -715,15 +715,16 @@ extern "C" int qg_viterbi (qg_ctx* ctx, const qg_dpconfig* cfg, size_t n_pairs, 
 }
 
 // ---- seam A: QuaffAligner::align (qmodel.cpp:2624-2646) = QuaffAlignmentTask::run for every read (qmodel.cpp:2764-2778)
-extern "C" int qg_align_reads (qg_ctx* ctx, const qg_dpconfig* cfg, const double* null_loglike,
-                               uint32_t* best_ref, double* score, uint32_t* x_start, uint32_t* x_end,
-                               uint8_t** path_out, uint64_t* path_offsets) {
+extern "C" int qg_align_reads_range (qg_ctx* ctx, const qg_dpconfig* cfg, size_t first_read, size_t n_reads, const double* null_loglike,
+                                     uint32_t* best_ref, double* score, uint32_t* x_start, uint32_t* x_end,
+                                     uint8_t** path_out, uint64_t* path_offsets) {
   if (!ctx || !cfg || !null_loglike || !best_ref || !score || !x_start || !x_end || !path_out || !path_offsets) return QG_ERR_INVALID;
   QG_TRY (qg_check_ready (ctx, cfg));
-  const size_t nx = ctx->seqs[QG_REFS].n, ny = ctx->seqs[QG_READS].n;
+  const size_t nx = ctx->seqs[QG_REFS].n, ny = n_reads;
+  if (first_read + n_reads > ctx->seqs[QG_READS].n) QG_FAIL (ctx, QG_ERR_INVALID, "read range exceeds the READS set");
   const size_t np = nx * ny;
   std::vector<uint32_t> xi (np), yi (np);
-  for (size_t y = 0; y < ny; ++y) for (size_t x = 0; x < nx; ++x) { xi[y * nx + x] = (uint32_t) x; yi[y * nx + x] = (uint32_t) y; }
+  for (size_t y = 0; y < ny; ++y) for (size_t x = 0; x < nx; ++x) { xi[y * nx + x] = (uint32_t) x; yi[y * nx + x] = (uint32_t) (first_read + y); }
   std::vector<double> sc (np);
   std::vector<uint32_t> xs (np), xe (np);
   std::vector<uint64_t> poff (np + 1);
@@ -752,6 +753,13 @@ extern "C" int qg_align_reads (qg_ctx* ctx, const qg_dpconfig* cfg, const double
   path_offsets[ny] = total;
   *path_out = paths;
   return QG_OK;
+}
+
+extern "C" int qg_align_reads (qg_ctx* ctx, const qg_dpconfig* cfg, const double* null_loglike,
+                               uint32_t* best_ref, double* score, uint32_t* x_start, uint32_t* x_end,
+                               uint8_t** path_out, uint64_t* path_offsets) {
+  if (!ctx) return QG_ERR_INVALID;
+  return qg_align_reads_range (ctx, cfg, 0, ctx->seqs[QG_READS].n, null_loglike, best_ref, score, x_start, x_end, path_out, path_offsets);
 }
 
 // ---- Forward --------------------------------------------------------------------------------------------------------

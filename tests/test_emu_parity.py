@@ -14,10 +14,15 @@ def emu(emu_lib):
     g.close()
 
 
-@pytest.fixture(scope="module")
+_CACHE = {}
+
+
+@pytest.fixture
 def workload(emu, oracle):
-    x, reads = pc.make_workload(ref_len=3000, n_reads=2, read_len=250, seed=3)
-    qp = pc.default_params()
+    if "w" not in _CACHE:
+        x, reads = pc.make_workload(ref_len=3000, n_reads=2, read_len=250, seed=3)
+        _CACHE["w"] = (x, reads, pc.default_params())
+    x, reads, qp = _CACHE["w"]
     emu.set_refs(x); emu.set_reads(reads); emu.set_params(qp)
     return x, reads, oracle.scores(qp)
 

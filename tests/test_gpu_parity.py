@@ -8,10 +8,16 @@ from quaff_b200 import api
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module")
+_CACHE = {}
+
+
+@pytest.fixture
 def workload(gpu, oracle):
-    x, reads = pc.make_workload(ref_len=60000, n_reads=6, read_len=2500, seed=11)
-    qp = pc.default_params()
+    """the context is shared by the whole session: (re)upload this module's inputs before every test"""
+    if "w" not in _CACHE:
+        x, reads = pc.make_workload(ref_len=60000, n_reads=6, read_len=2500, seed=11)
+        _CACHE["w"] = (x, reads, pc.default_params())
+    x, reads, qp = _CACHE["w"]
     gpu.set_refs(x); gpu.set_reads(reads); gpu.set_params(qp)
     return x, reads, oracle.scores(qp)
 
