@@ -14,8 +14,9 @@
 #define QG_SEED_CUH
 #include "qg_common.cuh"
 
-#define QG_SEED_THREADS 256
-#define QG_SEED_STEP 2048            // reference positions consumed between two emit scans
+#define QG_SEED_THREADS 512
+#define QG_SEED_PPT 8                // reference positions per thread per step
+#define QG_SEED_STEP (QG_SEED_THREADS * QG_SEED_PPT)   // reference positions consumed between two emit scans
 #define QG_SEED_CHUNK (192 * 1024)   // diagonals owned by one work item
 
 struct qg_seed_item {
@@ -69,7 +70,12 @@ __global__ void qg_codes_kernel (const uint8_t* __restrict__ tok, const uint64_t
 }
 
 // ---- the histogram kernel -------------------------------------------------------------------------
-// shared memory: cnt[ring] u32 | boff[nk+1] u16 | bpos[ymax] u16 | seedmask[STEP/32 + 2] u32 | small state
+// shared memory: cnt[ring] u32 | bkt[nk] u32 (start << 16 | length) | bpos[ymax] u16 | seedmask[STEP/32 + 2] u32
+// bpos holds, bucket by bucket, yLen - j for every k-mer start j of the read, so that a hit of reference position i
+// lands on ring slot (i + bpos) & (ring-1) = (d + yLen) & (ring-1) with one add and one and.
+// The full threshold scan of a finished window only runs if some counter of the block reached the threshold since the
+// last scan (the atomics return the old value); otherwise the window is just zeroed.
+template<bool COUNTS>
 __global__ void __launch_bounds__ (QG_SEED_THREADS)
 qg_seed_kernel (const qg_seed_item* __restrict__ items, const qg_pair_desc* __restrict__ pairs,
                 const uint16_t* __restrict__ xcodes, const uint16_t* __restrict__ ycodes,
@@ -79,13 +85,13 @@ qg_seed_kernel (const qg_seed_item* __restrict__ items, const qg_pair_desc* __re
   QG_DYN_SMEM (smem);
   const uint32_t nk = 1u << (2 * k);
   uint32_t* cnt = (uint32_t*) smem;
-  uint16_t* boff = (uint16_t*) (cnt + ring);
-  uint16_t* bpos = boff + ((nk + 2) & ~1u);
-  uint32_t* seedmask = (uint32_t*) (bpos + ((ymax + 1) & ~1u));
+  uint32_t* bkt = cnt + ring;
+  uint16_t* bpos = (uint16_t*) (bkt + nk);
+  uint32_t* seedmask = (uint32_t*) (bpos + ((ymax + 2) & ~1u));
   __shared__ uint32_t s_warp_tot[QG_SEED_THREADS / 32];
   __shared__ int s_open_lo, s_open_hi, s_have_open;
   __shared__ uint32_t s_nruns;
-  __shared__ int s_any;
+  __shared__ int s_any, s_hotmax;                            // s_hotmax: largest diagonal whose counter has reached the threshold
 
   const qg_seed_item it = items[blockIdx.x];
   const qg_pair_desc pd = pairs[it.pair];
@@ -98,12 +104,12 @@ qg_seed_kernel (const qg_seed_item* __restrict__ items, const qg_pair_desc* __re
 
   // -- 1. bucket index of the read: counting sort of k-mer start positions by k-mer code
   for (uint32_t c = tid; c < ring; c += QG_SEED_THREADS) cnt[c] = 0;
-  if (tid == 0) { s_have_open = 0; s_nruns = 0; s_open_lo = 0; s_open_hi = 0; s_any = 0; }
+  if (tid == 0) { s_have_open = 0; s_nruns = 0; s_open_lo = 0; s_open_hi = 0; s_any = 0; s_hotmax = -2147483647 - 1; }
   __syncthreads ();
   for (int j = tid; j < nyk; j += QG_SEED_THREADS) atomicAdd (&cnt[yc[j]], 1u);
   __syncthreads ();
   {
-    // exclusive scan of cnt[0..nk) -> boff; each thread owns a contiguous slice
+    // exclusive scan of cnt[0..nk) -> bucket starts; each thread owns a contiguous slice
     const uint32_t per = (nk + QG_SEED_THREADS - 1) / QG_SEED_THREADS;
     const uint32_t b = tid * per, e = (b + per < nk) ? b + per : nk;
     uint32_t sum = 0;
@@ -115,11 +121,10 @@ qg_seed_kernel (const qg_seed_item* __restrict__ items, const qg_pair_desc* __re
     uint32_t wbase = 0;
     for (int w = 0; w < wid; ++w) wbase += s_warp_tot[w];
     uint32_t run = wbase + incl - sum;
-    for (uint32_t c = b; c < e && c < nk; ++c) { const uint32_t v = cnt[c]; boff[c] = (uint16_t) run; cnt[c] = run; run += v; }
-    if (tid == QG_SEED_THREADS - 1) boff[nk] = (uint16_t) nyk;
+    for (uint32_t c = b; c < e && c < nk; ++c) { const uint32_t v = cnt[c]; bkt[c] = (run << 16) | v; cnt[c] = run; run += v; }
   }
   __syncthreads ();
-  for (int j = tid; j < nyk; j += QG_SEED_THREADS) { const uint32_t slot = atomicAdd (&cnt[yc[j]], 1u); bpos[slot] = (uint16_t) j; }
+  for (int j = tid; j < nyk; j += QG_SEED_THREADS) { const uint32_t slot = atomicAdd (&cnt[yc[j]], 1u); bpos[slot] = (uint16_t) (ylen - j); }
   __syncthreads ();
   for (uint32_t c = tid; c < ring; c += QG_SEED_THREADS) cnt[c] = 0;
   __syncthreads ();
@@ -127,69 +132,102 @@ qg_seed_kernel (const qg_seed_item* __restrict__ items, const qg_pair_desc* __re
   // -- 2. slide along the reference
   const int span = ylen - k;                              // largest j
   const int d_begin = it.d_begin, d_end = it.d_end;
-  int i_begin = d_begin > 0 ? d_begin : 0;
+  const int i_begin = d_begin > 0 ? d_begin : 0;
   int i_last = d_end - 1 + span;                          // inclusive
   if (i_last > xlen - k) i_last = xlen - k;
   const int min_diag = 1 - ylen, max_diag = xlen - 1;
+  const bool always_scan = COUNTS || threshold <= 1;
+  const uint32_t thr_m1 = (uint32_t) (threshold - 1);
+  const uint32_t dlen = (uint32_t) (d_end - d_begin);
   int emit_lo = d_begin;
-  unsigned long long my_hits = 0;
+  uint32_t my_hits = 0;
+  unsigned long long my_hits64 = 0;
 
   for (int i0 = i_begin; i0 <= i_last || emit_lo < d_end; i0 += QG_SEED_STEP) {
     const int i1 = (i0 + QG_SEED_STEP <= i_last + 1) ? i0 + QG_SEED_STEP : i_last + 1;    // exclusive
-    for (int i = i0 + tid; i < i1; i += QG_SEED_THREADS) {
-      const uint32_t code = xc[i];
-      if (code != 0xFFFFu) {
-        const uint32_t b0 = boff[code], b1 = boff[code + 1];
-        for (uint32_t b = b0; b < b1; ++b) {
-          const int d = i - (int) bpos[b];
-          if (d >= d_begin && d < d_end) { atomicAdd (&cnt[(uint32_t) (d + ylen) & mask], 1u); ++my_hits; }
+    uint32_t code[QG_SEED_PPT];
+#pragma unroll
+    for (int r = 0; r < QG_SEED_PPT; ++r) { const int i = i0 + r * QG_SEED_THREADS + tid; code[r] = (i < i1) ? (uint32_t) xc[i] : 0xFFFFu; }
+    int hotd = -2147483647 - 1;
+#pragma unroll
+    for (int r = 0; r < QG_SEED_PPT; ++r) {
+      if (code[r] != 0xFFFFu) {
+        const int i = i0 + r * QG_SEED_THREADS + tid;
+        const uint32_t e = bkt[code[r]];
+        const uint16_t* bp = bpos + (e >> 16);
+        const uint32_t len = e & 0xFFFFu;
+        if (i >= d_begin + span && i < d_end) {           // every diagonal this position can hit belongs to the item
+          for (uint32_t t = 0; t < len; ++t) {
+            const int sd = i + (int) bp[t];                 // d + yLen
+            const uint32_t old = atomicAdd (&cnt[(uint32_t) sd & mask], 1u);
+            if (old == thr_m1 && sd - ylen > hotd) hotd = sd - ylen;
+          }
+          my_hits += len;
+        } else {
+          const uint32_t ib = (uint32_t) (i - ylen - d_begin);     // d - d_begin = ib + bp[t]
+          for (uint32_t t = 0; t < len; ++t) {
+            const uint32_t v = bp[t];
+            if (ib + v < dlen) {
+              const int sd = i + (int) v;
+              const uint32_t old = atomicAdd (&cnt[(uint32_t) sd & mask], 1u);
+              if (old == thr_m1 && sd - ylen > hotd) hotd = sd - ylen;
+              ++my_hits;
+            }
+          }
         }
       }
     }
+    if (hotd != -2147483647 - 1) atomicMax (&s_hotmax, hotd);
+    if (my_hits > 0x40000000u) { my_hits64 += my_hits; my_hits = 0; }
     __syncthreads ();
     // diagonals below i1 - span can receive no further hits
     int emit_hi = (i1 > i_last) ? d_end : i1 - span;
     if (emit_hi > d_end) emit_hi = d_end;
     if (emit_hi > emit_lo) {
-      const int ngroups = (emit_hi - emit_lo + 31) / 32;   // <= STEP/32 + 1 except for the final flush
-      for (int g0 = 0; g0 < ngroups; g0 += QG_SEED_STEP / 32) {
-        const int gcount = (ngroups - g0 < QG_SEED_STEP / 32) ? ngroups - g0 : QG_SEED_STEP / 32;
-        for (int g = wid; g < gcount; g += QG_SEED_THREADS / 32) {
-          const int d = emit_lo + (g0 + g) * 32 + lane;
-          uint32_t c = 0;
-          if (d < emit_hi) {
-            const uint32_t idx = (uint32_t) (d + ylen) & mask; c = cnt[idx]; cnt[idx] = 0;
-            if (counts_out) { counts_out[pd.count_off + (uint64_t) (d + span)] = c; c = 0; }      // memory-guided mode: raw counts only
+      if (always_scan || s_hotmax >= emit_lo) {         // a diagonal at or beyond emit_lo has reached the threshold
+        const int ngroups = (emit_hi - emit_lo + 31) / 32;
+        for (int g0 = 0; g0 < ngroups; g0 += QG_SEED_STEP / 32) {
+          const int gcount = (ngroups - g0 < QG_SEED_STEP / 32) ? ngroups - g0 : QG_SEED_STEP / 32;
+          for (int g = wid; g < gcount; g += QG_SEED_THREADS / 32) {
+            const int d = emit_lo + (g0 + g) * 32 + lane;
+            uint32_t c = 0;
+            if (d < emit_hi) {
+              const uint32_t idx = (uint32_t) (d + ylen) & mask; c = cnt[idx]; cnt[idx] = 0;
+              if (COUNTS) { counts_out[pd.count_off + (uint64_t) (d + span)] = c; c = 0; }      // memory-guided mode: raw counts only
+            }
+            const uint32_t m = __ballot_sync (QG_FULL_MASK, d < emit_hi && (int) c >= threshold && c > 0);
+            if (lane == 0) { seedmask[g] = m; if (m) s_any = 1; }
           }
-          const uint32_t m = __ballot_sync (QG_FULL_MASK, d < emit_hi && (int) c >= threshold && c > 0);
-          if (lane == 0) { seedmask[g] = m; if (m) s_any = 1; }
-        }
-        __syncthreads ();
-        if (tid == 0 && s_any) {
-          s_any = 0;
-          // seeds in ascending order -> union of [seed-half, seed+half] clipped to the matrix (diagenv.cpp:79-84)
-          int open_lo = s_open_lo, open_hi = s_open_hi, have = s_have_open;
-          uint32_t nr = s_nruns;
-          for (int g = 0; g < gcount; ++g) {
-            uint32_t m = seedmask[g];
-            while (m) {
-              const int b = __ffs ((int) m) - 1;
-              m &= m - 1;
-              const int seed = emit_lo + (g0 + g) * 32 + b;
-              int lo = seed - half_band, hi = seed + half_band;
-              if (lo < min_diag) lo = min_diag;
-              if (hi > max_diag) hi = max_diag;
-              if (have && lo <= open_hi + 1) { if (hi > open_hi) open_hi = hi; }
-              else {
-                if (have) { if (nr < run_cap) item_runs[(size_t) blockIdx.x * run_cap + nr] = make_int2 (open_lo, open_hi); else *overflow_flag = 1; ++nr; }
-                open_lo = lo; open_hi = hi; have = 1;
+          __syncthreads ();
+          if (tid == 0 && s_any) {
+            s_any = 0;
+            // seeds in ascending order -> union of [seed-half, seed+half] clipped to the matrix (diagenv.cpp:79-84)
+            int open_lo = s_open_lo, open_hi = s_open_hi, have = s_have_open;
+            uint32_t nr = s_nruns;
+            for (int g = 0; g < gcount; ++g) {
+              uint32_t m = seedmask[g];
+              while (m) {
+                const int b = __ffs ((int) m) - 1;
+                m &= m - 1;
+                const int seed = emit_lo + (g0 + g) * 32 + b;
+                int lo = seed - half_band, hi = seed + half_band;
+                if (lo < min_diag) lo = min_diag;
+                if (hi > max_diag) hi = max_diag;
+                if (have && lo <= open_hi + 1) { if (hi > open_hi) open_hi = hi; }
+                else {
+                  if (have) { if (nr < run_cap) item_runs[(size_t) blockIdx.x * run_cap + nr] = make_int2 (open_lo, open_hi); else *overflow_flag = 1; ++nr; }
+                  open_lo = lo; open_hi = hi; have = 1;
+                }
               }
             }
+            s_open_lo = open_lo; s_open_hi = open_hi; s_have_open = have; s_nruns = nr;
           }
-          s_open_lo = open_lo; s_open_hi = open_hi; s_have_open = have; s_nruns = nr;
+          __syncthreads ();
         }
-        __syncthreads ();
+      } else {
+        for (int d = emit_lo + tid; d < emit_hi; d += QG_SEED_THREADS) cnt[(uint32_t) (d + ylen) & mask] = 0;
       }
+      __syncthreads ();
       emit_lo = emit_hi;
     }
     if (i1 > i_last && emit_lo >= d_end) break;
@@ -200,8 +238,9 @@ qg_seed_kernel (const qg_seed_item* __restrict__ items, const qg_pair_desc* __re
     item_nruns[blockIdx.x] = nr < run_cap ? nr : run_cap;
   }
   // hit statistics
-  for (int o = 16; o > 0; o >>= 1) my_hits += __shfl_down_sync (QG_FULL_MASK, my_hits, o);
-  if (lane == 0 && my_hits) atomicAdd (hit_counter, my_hits);
+  my_hits64 += my_hits;
+  for (int o = 16; o > 0; o >>= 1) my_hits64 += __shfl_down_sync (QG_FULL_MASK, my_hits64, o);
+  if (lane == 0 && my_hits64) atomicAdd (hit_counter, my_hits64);
 }
 
 // ---- merge item runs of a pair, add diagonal 0, count cells ---------------------------------------

@@ -332,13 +332,15 @@ static int qg_envelope_stage_cap (qg_ctx* ctx, const qg_dpconfig* cfg, uint64_t 
     const uint32_t nk = 1u << (2 * k);
     uint32_t need = std::max<uint32_t> (nk, QG_SEED_STEP + ymax + 1), ring = 1;
     while (ring < need) ring <<= 1;
-    const size_t smem = (size_t) ring * 4 + (size_t) ((nk + 2) & ~1u) * 2 + (size_t) ((ymax + 1) & ~1u) * 2 + (QG_SEED_STEP / 32 + 2) * 4;
+    const size_t smem = (size_t) ring * 4 + (size_t) nk * 4 + (size_t) ((ymax + 2) & ~1u) * 2 + (QG_SEED_STEP / 32 + 2) * 4;
     if (smem > ctx->smem_optin)
       QG_FAIL (ctx, QG_ERR_UNSUPPORTED, "reads of up to %u bases need %zu B of shared memory per seeding CTA (limit %zu)", ymax, smem, ctx->smem_optin);
-    QG_CUDA (ctx, cudaFuncSetAttribute (qg_seed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    QG_CUDA (ctx, cudaFuncSetAttribute (qg_seed_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    QG_CUDA (ctx, cudaFuncSetAttribute (qg_seed_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
     {
       qg_timer tm (ctx, &ctx->stats.ms_seed);
-      QG_LAUNCH (qg_seed_kernel, (unsigned) items.size (), QG_SEED_THREADS, smem, ctx->stream,
+      auto kfn = memory_mode ? qg_seed_kernel<true> : qg_seed_kernel<false>;
+      QG_LAUNCH (kfn, (unsigned) items.size (), QG_SEED_THREADS, smem, ctx->stream,
                  dIT.as<qg_seed_item> (), dPD.as<qg_pair_desc> (), ctx->seqs[x_set].d_codes.as<uint16_t> (), ctx->seqs[QG_READS].d_codes.as<uint16_t> (),
                  k, cfg->kmer_threshold, (int) ((unsigned) cfg->band_size / 2), ring, ymax, run_cap,
                  dIR.as<int2> (), dIN.as<uint32_t> (), (unsigned long long*) ((char*) dFL.p + 8), (uint32_t*) dFL.p,
