@@ -264,7 +264,7 @@ def main():
     # ---- side measurement: Forward / Backward (train) GCUPS on a slice of the same reads ---------------------------
     train = None
     if not args.no_train:
-        nt = min(B, 192)
+        nt = min(B, 768)
         G.set_reads(batches[0][:nt])
         xi = np.tile(np.arange(2, dtype=np.uint32), nt); yi = np.repeat(np.arange(nt, dtype=np.uint32), 2)
         G.forward(cfg, xi, yi)
@@ -278,7 +278,7 @@ def main():
         train = {"pairs": int(len(xi)), "forward_gcups": cu_f / 1e9 / (s1["ms_forward"] / 1e3),
                  "backward_gcups": cu_b / 1e9 / (s2["ms_backward"] / 1e3),
                  "fwd_bwd_gcups": 2 * cu_b / 1e9 / ((s2["ms_forward"] + s2["ms_backward"]) / 1e3),
-                 "formulation": "FP64 log space, the reference's table log-sum-exp (bit-exact Forward)"}
+                 "formulation": "FP64 probability space with the reference's log-sum-exp cut-off (default); the bit-exact log-space kernels are selectable (QG_OPT_FB_EXACT)"}
 
     # ---- reduce over ranks: the slowest rank defines the step -----------------------------------------------------
     times = torch.tensor([dt, dt_e], dtype=torch.float64, device="cuda")

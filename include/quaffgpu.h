@@ -96,6 +96,11 @@ const char* qg_last_error (const qg_ctx* ctx);   /* ctx may be NULL: last qg_cre
 void qg_free (void* p);
 int  qg_abi_version (void);
 
+/* options */
+#define QG_OPT_FB_EXACT 1         /* 1: Forward/Backward with the reference's table log-sum-exp in log space (bit-exact
+                                     Forward); 0 (default): probability-space FP64 kernels, ~1e-8 relative to the reference */
+int  qg_set_option (qg_ctx* ctx, int option, int64_t value);
+
 /* ---- inputs ----------------------------------------------------------------------------------- */
 /* tok: concatenated tokens in {0,1,2,3}; qual: concatenated quality scores in 0..93 or NULL when the
  * set carries no qualities; offsets[n+1].  Replaces whatever the set held before.                   */

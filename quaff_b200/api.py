@@ -30,7 +30,7 @@ c_u64_p = C.POINTER(C.c_uint64)
 
 # every symbol include/quaffgpu.h declares (checked by tests/test_abi.py against the header text)
 ABI_SYMBOLS = [
-    "qg_counts_size", "qg_create", "qg_destroy", "qg_last_error", "qg_free", "qg_abi_version", "qg_set_seqs",
+    "qg_counts_size", "qg_create", "qg_set_option", "qg_destroy", "qg_last_error", "qg_free", "qg_abi_version", "qg_set_seqs",
     "qg_set_align_model", "qg_scores_from_params", "qg_null_loglike", "qg_envelopes", "qg_viterbi", "qg_forward",
     "qg_backward_counts", "qg_align_reads", "qg_align_reads_range", "qg_estep", "qg_set_overlap_model", "qg_overlap_viterbi", "qg_overlap_rows",
     "qg_overlap_reads", "qg_get_stats",
@@ -181,6 +181,14 @@ class QuaffGPU:
     def _check(self, rc: int):
         if rc != 0:
             raise QuaffGpuError(rc, (self.L.qg_last_error(self.ctx) or b"").decode())
+
+    def set_option(self, option: int, value: int):
+        self._check(self.L.qg_set_option(self.ctx, int(option), C.c_int64(int(value))))
+
+    def set_fb_exact(self, exact: bool):
+        """True: log-space Forward/Backward with the reference's table log-sum-exp (bit-exact Forward);
+        False (default): probability-space kernels"""
+        self.set_option(1, 1 if exact else 0)
 
     # ---- inputs ---------------------------------------------------------------------------------
     def set_seqs_raw(self, which: int, tok: np.ndarray, qual: Optional[np.ndarray], off: np.ndarray):

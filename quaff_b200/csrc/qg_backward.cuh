@@ -33,7 +33,7 @@ qg_backward_kernel (const qg_fill_args a) {
   const uint64_t* xw = a.xpacked + a.xpoff[sg.xseq];
   const int nxw = (xlen + 31) >> 5;
   const qg_rowp* rp = a.rp + sg.rp_off;
-  const double* st = a.store + sg.store_off;
+  const double* stbase = a.store + sg.store_off;
   const double i2i = a.i2i, i2m = a.i2m, d2d = a.d2d, d2m = a.d2m;
   const bool local = a.local != 0;
   const double m2e = rp[0].m2m;
@@ -114,8 +114,10 @@ qg_backward_kernel (const qg_fill_args a) {
       double BD = qg_lse (a.lse, cDM, cDD);
       if (!ok) { BM = QG_NEG_INF; BI = QG_NEG_INF; BD = QG_NEG_INF; }
       if (ok && zok) {
-        const uint64_t rowb = (uint64_t) j * 3 * SW;
-        const double fM = st[rowb + s], fI = st[rowb + SW + s], fD = st[rowb + 2 * (uint64_t) SW + s];
+        // Forward wrote cell (slot s, row j) at macro-step j + fvl by virtual lane fvl = s / R, position s % R
+        const int fvl = s / R, fc = s - fvl * R;
+        const double* st = stbase + ((uint64_t) (j + fvl) * (32 * NW) + fvl) * (3 * R);
+        const double fM = st[fc], fI = st[R + fc], fD = st[2 * R + fc];
         const double n_m2m = exp ((fM + cM) - Z), n_i2m = exp ((fI + cIM) - Z), n_d2m = exp ((fD + cDM) - Z);
         const double n_m2i = exp ((fM + cI) - Z), n_i2i = exp ((fI + cII) - Z);
         const double n_m2d = exp ((fM + cD) - Z), n_d2d = exp ((fD + cDD) - Z);

@@ -107,6 +107,8 @@ struct qg_ctx {
   size_t smem_optin = 0;
   cudaStream_t stream = 0;
   cudaEvent_t ev[2] = {0, 0};
+  cudaStream_t side[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // launch classes of one stage run concurrently on these
+  cudaEvent_t ev_fork = 0, ev_join[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   qg_error err;
   qg_seqset seqs[2];
   qg_model_dev model;
@@ -114,7 +116,8 @@ struct qg_ctx {
   qg_dbuf d_lse;                     // the 100001-entry FP64 log-sum-exp table (logsumexp.cpp:20-28)
   qg_stats stats;
   // scratch, grown on demand and reused across calls
-  qg_dbuf scratch[24];
+  qg_dbuf scratch[40];
+  int fb_exact = 0;                  // QG_OPT_FB_EXACT
 };
 
 static inline int qg_reserve (qg_ctx* ctx, qg_dbuf& b, size_t bytes) {

@@ -256,14 +256,11 @@ qg_fill_kernel (const qg_fill_args a) {
     }
     if (MODE == 0) a.trace[sg.trace_off + (uint64_t) u * (32 * NW) + vl] = tword;
     if (MODE == 2 && active) {
-      double* st = a.store + sg.store_off;
-      const uint64_t rowb = (uint64_t) j * 3 * SW;
+      // skewed layout [macro-step][virtual lane][state][c]: one contiguous 24 R byte record per lane, a warp writes one
+      // contiguous block per macro-step, and Backward (mirrored) reads exactly one such block per macro-step
+      double* st = a.store + sg.store_off + ((uint64_t) u * (32 * NW) + vl) * (3 * R);
 #pragma unroll
-      for (int c = 0; c < R; ++c) {
-        st[rowb + s0 + c] = M[c];
-        st[rowb + SW + s0 + c] = I[c];
-        st[rowb + 2 * (uint64_t) SW + s0 + c] = D[c];
-      }
+      for (int c = 0; c < R; ++c) { st[c] = M[c]; st[R + c] = I[c]; st[2 * R + c] = D[c]; }
     }
   }
 

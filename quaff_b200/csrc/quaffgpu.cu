@@ -6,6 +6,7 @@
 #include "qg_dp.cuh"
 #include "qg_backward.cuh"
 #include "qg_overlap.cuh"
+#include "qg_prob.cuh"
 #include <map>
 #include <numeric>
 
@@ -14,7 +15,7 @@ static qg_error g_create_error;
 enum {
   SC_PAIRDESC = 0, SC_ITEMS, SC_ITEMRUNS, SC_ITEMNRUNS, SC_PAIRRUNS, SC_PAIRINFO, SC_PAIRCU, SC_FLAGS,
   SC_SEGS, SC_RPJOBS, SC_RP, SC_TRACE, SC_ENDVALS, SC_PAIRDP, SC_OUT0, SC_OUT1, SC_OUT2, SC_OUT3, SC_PATHSCR, SC_PATHOUT,
-  SC_STORE, SC_ROWACC, SC_MISC0, SC_MISC1
+  SC_STORE, SC_ROWACC, SC_MISC0, SC_MISC1, SC_RQ, SC_RS, SC_ENDEX, SC_STOREEX, SC_ZM, SC_ZE
 };
 
 // ---- small helpers -----------------------------------------------------------------------------------
@@ -44,6 +45,20 @@ struct qg_timer {
     *acc += ms;
   }
 };
+// the launch classes of one DP stage (different R / warp counts) are independent: run them side by side
+static int qg_fork (qg_ctx* ctx) { QG_CUDA (ctx, cudaEventRecord (ctx->ev_fork, ctx->stream)); return QG_OK; }
+static int qg_side (qg_ctx* ctx, int k, cudaStream_t* out) {
+  *out = ctx->side[k & 7];
+  if (k < 8) QG_CUDA (ctx, cudaStreamWaitEvent (*out, ctx->ev_fork, 0));
+  return QG_OK;
+}
+static int qg_join (qg_ctx* ctx, int n) {
+  for (int i = 0; i < n && i < 8; ++i) {
+    QG_CUDA (ctx, cudaEventRecord (ctx->ev_join[i], ctx->side[i]));
+    QG_CUDA (ctx, cudaStreamWaitEvent (ctx->stream, ctx->ev_join[i], 0));
+  }
+  return QG_OK;
+}
 static size_t qg_env_size (const char* name, size_t dflt) {
   const char* v = getenv (name);
   return (v && *v) ? (size_t) strtoull (v, nullptr, 10) : dflt;
@@ -86,6 +101,11 @@ extern "C" int qg_create (qg_ctx** out, int device) {
   if ((e = cudaStreamCreateWithFlags (&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail ("cudaStreamCreate", e);
   if ((e = cudaEventCreate (&ctx->ev[0])) != cudaSuccess) return fail ("cudaEventCreate", e);
   if ((e = cudaEventCreate (&ctx->ev[1])) != cudaSuccess) return fail ("cudaEventCreate", e);
+  if ((e = cudaEventCreateWithFlags (&ctx->ev_fork, cudaEventDisableTiming)) != cudaSuccess) return fail ("cudaEventCreate", e);
+  for (int i = 0; i < 8; ++i) {
+    if ((e = cudaStreamCreateWithFlags (&ctx->side[i], cudaStreamNonBlocking)) != cudaSuccess) return fail ("cudaStreamCreate", e);
+    if ((e = cudaEventCreateWithFlags (&ctx->ev_join[i], cudaEventDisableTiming)) != cudaSuccess) return fail ("cudaEventCreate", e);
+  }
   // the reference's log-sum-exp table, built with the host libm exactly as logsumexp.cpp:20-28 does
   {
     const int n = ((int) (10 / .0001)) + 1;
@@ -111,8 +131,16 @@ extern "C" void qg_destroy (qg_ctx* ctx) {
   rel (ctx->d_lse);
   for (auto& b : ctx->scratch) rel (b);
   cudaEventDestroy (ctx->ev[0]); cudaEventDestroy (ctx->ev[1]);
+  cudaEventDestroy (ctx->ev_fork);
+  for (int i = 0; i < 8; ++i) { cudaStreamDestroy (ctx->side[i]); cudaEventDestroy (ctx->ev_join[i]); }
   cudaStreamDestroy (ctx->stream);
   delete ctx;
+}
+
+extern "C" int qg_set_option (qg_ctx* ctx, int option, int64_t value) {
+  if (!ctx) return QG_ERR_INVALID;
+  if (option == QG_OPT_FB_EXACT) { ctx->fb_exact = value ? 1 : 0; return QG_OK; }
+  QG_FAIL (ctx, QG_ERR_INVALID, "unknown option %d", option);
 }
 
 extern "C" int qg_get_stats (qg_ctx* ctx, qg_stats* out, int reset) {
@@ -481,7 +509,7 @@ static int qg_build_plan (qg_ctx* ctx, const qg_env_result& er, size_t p0, size_
       const uint64_t lanes = 32ull * nw;
       if (mode == 0 || mode == 3) { sg.trace_off = plan.trace_words; plan.trace_words += ((uint64_t) pp.ylen + lanes + 1) * lanes; }
       if (mode == 3) { sg.acc_off = plan.acc_rows; plan.acc_rows += (uint64_t) pp.ylen + 2; }
-      if (mode == 2) { sg.store_off = plan.store_doubles; plan.store_doubles += ((uint64_t) pp.ylen + 1) * 3 * lanes * R;
+      if (mode == 2) { sg.store_off = plan.store_doubles; plan.store_doubles += ((uint64_t) pp.ylen + lanes + 1) * 3 * lanes * R;
                        sg.acc_off = plan.acc_rows; plan.acc_rows += (uint64_t) pp.ylen + 2; }
       sg.seg_id = plan.segs.size ();
       if (mode == 0) sg.aux_off = plan.segs.size ();           // Viterbi: index of the segment in pair order
@@ -508,13 +536,16 @@ static int qg_build_plan (qg_ctx* ctx, const qg_env_result& er, size_t p0, size_
 
 template<int MODE>
 static int qg_launch_fill (qg_ctx* ctx, const qg_dp_plan& plan, qg_fill_args a, const qg_segment* d_segs_launch_order) {
+  QG_TRY (qg_fork (ctx));
+  int kcls = 0;
   for (const auto& L : plan.launches) {
+    cudaStream_t st; QG_TRY (qg_side (ctx, kcls++, &st));
     a.segs = d_segs_launch_order + L.begin;
     const bool multi = L.nw > 1;
     const unsigned block = 32u * L.nw;
 #define QG_CASE(RR) case RR: \
-      if (multi) { auto kfn = qg_fill_kernel<8, MODE, true>; QG_LAUNCH (kfn, L.count, block, 0, ctx->stream, a); } \
-      else { auto kfn = qg_fill_kernel<RR, MODE, false>; QG_LAUNCH (kfn, L.count, block, 0, ctx->stream, a); } break;
+      if (multi) { auto kfn = qg_fill_kernel<8, MODE, true>; QG_LAUNCH (kfn, L.count, block, 0, st, a); } \
+      else { auto kfn = qg_fill_kernel<RR, MODE, false>; QG_LAUNCH (kfn, L.count, block, 0, st, a); } break;
     switch (L.R) {
       QG_CASE (2) QG_CASE (3) QG_CASE (4) QG_CASE (5) QG_CASE (6) QG_CASE (7) QG_CASE (8)
       default: QG_FAIL (ctx, QG_ERR_INVALID, "internal: unsupported R=%d", L.R);
@@ -522,6 +553,7 @@ static int qg_launch_fill (qg_ctx* ctx, const qg_dp_plan& plan, qg_fill_args a, 
 #undef QG_CASE
     QG_TRY (qg_check_launch (ctx, "qg_fill_kernel"));
   }
+  QG_TRY (qg_join (ctx, kcls));
   return QG_OK;
 }
 
@@ -764,6 +796,56 @@ extern "C" int qg_align_reads (qg_ctx* ctx, const qg_dpconfig* cfg, const double
   return qg_align_reads_range (ctx, cfg, 0, ctx->seqs[QG_READS].n, null_loglike, best_ref, score, x_start, x_end, path_out, path_offsets);
 }
 
+// ---- probability-space Forward / Backward (qg_prob.cuh): used unless QG_OPT_FB_EXACT or a run needs several warps ----
+static bool qg_plan_single_warp (const qg_dp_plan& plan) {
+  for (const auto& L : plan.launches) if (L.nw > 1) return false;
+  return true;
+}
+
+static int qg_stage_rowq (qg_ctx* ctx, const qg_dp_plan& plan) {
+  QG_TRY (qg_reserve (ctx, ctx->scratch[SC_RQ], sizeof (qg_rowq) * (plan.rp_rows + 1)));
+  QG_TRY (qg_reserve (ctx, ctx->scratch[SC_RS], sizeof (double) * (plan.rp_rows + 1)));
+  if (!plan.rp_jobs.empty ()) {
+    QG_LAUNCH (qg_rowq_kernel, (unsigned) plan.rp_jobs.size (), 256, 0, ctx->stream,
+               ctx->scratch[SC_RPJOBS].as<qg_rp_job> (), ctx->scratch[SC_RP].as<qg_rowp> (), ctx->scratch[SC_RQ].as<qg_rowq> (), ctx->scratch[SC_RS].as<double> ());
+    QG_TRY (qg_check_launch (ctx, "qg_rowq_kernel"));
+  }
+  return QG_OK;
+}
+
+static qg_prob_args qg_prob_base_args (qg_ctx* ctx, const qg_dpconfig* cfg, int x_set) {
+  qg_prob_args a;
+  memset (&a, 0, sizeof (a));
+  a.xpacked = ctx->seqs[x_set].d_packed.as<uint64_t> ();
+  a.xpoff = ctx->seqs[x_set].d_poff.as<uint64_t> ();
+  a.rq = ctx->scratch[SC_RQ].as<qg_rowq> ();
+  a.rs = ctx->scratch[SC_RS].as<double> ();
+  a.pi2i = exp (ctx->model.i2i); a.pi2m = exp (ctx->model.i2m); a.pd2d = exp (ctx->model.d2d); a.pd2m = exp (ctx->model.d2m);
+  a.local = cfg->local;
+  return a;
+}
+
+template<int BACKWARD>
+static int qg_launch_prob (qg_ctx* ctx, const qg_dp_plan& plan, qg_prob_args a, const qg_segment* d_segs_launch_order) {
+  QG_TRY (qg_fork (ctx));
+  int kcls = 0;
+  for (const auto& L : plan.launches) {
+    cudaStream_t st; QG_TRY (qg_side (ctx, kcls++, &st));
+    a.segs = d_segs_launch_order + L.begin;
+#define QG_CASE(RR) case RR: \
+      if (BACKWARD) { auto kfn = qg_backward_prob_kernel<RR>; QG_LAUNCH (kfn, L.count, 32, 0, st, a); } \
+      else { auto kfn = qg_forward_prob_kernel<RR>; QG_LAUNCH (kfn, L.count, 32, 0, st, a); } break;
+    switch (L.R) {
+      QG_CASE (2) QG_CASE (3) QG_CASE (4) QG_CASE (5) QG_CASE (6) QG_CASE (7) QG_CASE (8)
+      default: QG_FAIL (ctx, QG_ERR_INVALID, "internal: unsupported R=%d", L.R);
+    }
+#undef QG_CASE
+    QG_TRY (qg_check_launch (ctx, BACKWARD ? "qg_backward_prob_kernel" : "qg_forward_prob_kernel"));
+  }
+  QG_TRY (qg_join (ctx, kcls));
+  return QG_OK;
+}
+
 // ---- Forward --------------------------------------------------------------------------------------------------------
 extern "C" int qg_forward (qg_ctx* ctx, const qg_dpconfig* cfg, size_t n_pairs, const uint32_t* xi, const uint32_t* yi, double* loglike) {
   if (!ctx || !cfg || !xi || !yi || !loglike) return QG_ERR_INVALID;
@@ -785,7 +867,25 @@ extern "C" int qg_forward (qg_ctx* ctx, const qg_dpconfig* cfg, size_t n_pairs, 
   }
   ctx->stats.n_segments += plan.segs.size ();
   ctx->stats.cell_updates += qg_plan_cells (er, 0, n_pairs);
-  {
+  const bool fast = !ctx->fb_exact && qg_plan_single_warp (plan);
+  if (fast) {
+    {
+      qg_timer tm (ctx, &ctx->stats.ms_prep);
+      QG_TRY (qg_stage_rowq (ctx, plan));
+      QG_TRY (qg_reserve (ctx, ctx->scratch[SC_ENDEX], sizeof (int) * (plan.aux_slots + 1)));
+      QG_TRY (qg_reserve (ctx, ctx->scratch[SC_ZM], sizeof (double) * (n_pairs + 1)));
+      QG_TRY (qg_reserve (ctx, ctx->scratch[SC_ZE], sizeof (int) * (n_pairs + 1)));
+    }
+    qg_timer tm (ctx, &ctx->stats.ms_forward);
+    qg_prob_args a = qg_prob_base_args (ctx, cfg, QG_REFS);
+    a.endvals = ctx->scratch[SC_ENDVALS].as<double> (); a.endex = ctx->scratch[SC_ENDEX].as<int> ();
+    QG_TRY (qg_launch_prob<0> (ctx, plan, a, ctx->scratch[SC_SEGS].as<qg_segment> ()));
+    QG_LAUNCH (qg_forward_prob_finalize_kernel, (unsigned) ((n_pairs + 63) / 64), 64, 0, ctx->stream,
+               ctx->scratch[SC_PAIRDP].as<qg_pair_dp> (), (uint32_t) n_pairs, ctx->scratch[SC_MISC0].as<qg_segment> (),
+               ctx->scratch[SC_ENDVALS].as<double> (), ctx->scratch[SC_ENDEX].as<int> (), ctx->scratch[SC_RS].as<double> (),
+               ctx->scratch[SC_OUT0].as<double> (), ctx->scratch[SC_ZM].as<double> (), ctx->scratch[SC_ZE].as<int> ());
+    QG_TRY (qg_check_launch (ctx, "qg_forward_prob_finalize_kernel"));
+  } else {
     qg_timer tm (ctx, &ctx->stats.ms_forward);
     qg_fill_args a = qg_base_args (ctx, cfg, QG_REFS);
     a.endvals = ctx->scratch[SC_ENDVALS].as<double> ();
@@ -805,13 +905,16 @@ extern "C" int qg_forward (qg_ctx* ctx, const qg_dpconfig* cfg, size_t n_pairs, 
 // ---- Backward + counts ----------------------------------------------------------------------------------------------
 template<int DUMMY>
 static int qg_launch_backward (qg_ctx* ctx, const qg_dp_plan& plan, qg_fill_args a, const qg_segment* d_segs_launch_order) {
+  QG_TRY (qg_fork (ctx));
+  int kcls = 0;
   for (const auto& L : plan.launches) {
+    cudaStream_t st; QG_TRY (qg_side (ctx, kcls++, &st));
     a.segs = d_segs_launch_order + L.begin;
     const bool multi = L.nw > 1;
     const unsigned block = 32u * L.nw;
 #define QG_CASE(RR) case RR: \
-      if (multi) { auto kfn = qg_backward_kernel<8, true>; QG_LAUNCH (kfn, L.count, block, 0, ctx->stream, a); } \
-      else { auto kfn = qg_backward_kernel<RR, false>; QG_LAUNCH (kfn, L.count, block, 0, ctx->stream, a); } break;
+      if (multi) { auto kfn = qg_backward_kernel<8, true>; QG_LAUNCH (kfn, L.count, block, 0, st, a); } \
+      else { auto kfn = qg_backward_kernel<RR, false>; QG_LAUNCH (kfn, L.count, block, 0, st, a); } break;
     switch (L.R) {
       QG_CASE (2) QG_CASE (3) QG_CASE (4) QG_CASE (5) QG_CASE (6) QG_CASE (7) QG_CASE (8)
       default: QG_FAIL (ctx, QG_ERR_INVALID, "internal: unsupported R=%d", L.R);
@@ -819,6 +922,7 @@ static int qg_launch_backward (qg_ctx* ctx, const qg_dp_plan& plan, qg_fill_args
 #undef QG_CASE
     QG_TRY (qg_check_launch (ctx, "qg_backward_kernel"));
   }
+  QG_TRY (qg_join (ctx, kcls));
   return QG_OK;
 }
 
@@ -847,7 +951,7 @@ extern "C" int qg_backward_counts (qg_ctx* ctx, const qg_dpconfig* cfg, size_t n
       for (uint32_t r = er.run_begin[p1]; r < er.run_begin[p1 + 1]; ++r) {
         int R, nw; const uint32_t width = (uint32_t) (er.runs[r].y - er.runs[r].x + 1);
         if (qg_pick_R (width, &R, &nw) != QG_OK) QG_FAIL (ctx, QG_ERR_UNSUPPORTED, "pair %zu: a run of %u consecutive diagonals exceeds the %d this build fills with one CTA", p1, width, 256 * QG_MAX_NW);
-        b += ((uint64_t) Y.len (yi[p1]) + 1) * 3 * 32ull * nw * R * 8 + ((uint64_t) Y.len (yi[p1]) + 2) * 64;
+        b += ((uint64_t) Y.len (yi[p1]) + 32ull * nw + 1) * 3 * 32ull * nw * R * 8 + ((uint64_t) Y.len (yi[p1]) + 2) * 64;
       }
       if (p1 > p0 && bytes + b > budget) break;
       bytes += b; ++p1;
@@ -876,6 +980,42 @@ extern "C" int qg_backward_counts (qg_ctx* ctx, const qg_dpconfig* cfg, size_t n
     ctx->stats.n_segments += plan.segs.size ();
     ctx->stats.cell_updates += 2 * qg_plan_cells (er, p0, p1);
     ctx->stats.fwd_store_bytes += plan.store_doubles * 8;
+    const bool fast = !ctx->fb_exact && qg_plan_single_warp (plan);
+    if (fast) {
+      {
+        qg_timer tm (ctx, &ctx->stats.ms_prep);
+        QG_TRY (qg_stage_rowq (ctx, plan));
+        QG_TRY (qg_reserve (ctx, ctx->scratch[SC_ENDEX], sizeof (int) * (plan.aux_slots + 1)));
+        QG_TRY (qg_reserve (ctx, ctx->scratch[SC_STOREEX], sizeof (int) * 32 * (plan.acc_rows + 32 * plan.segs.size () + 1)));
+        QG_TRY (qg_reserve (ctx, ctx->scratch[SC_ZM], sizeof (double) * (np + 1)));
+        QG_TRY (qg_reserve (ctx, ctx->scratch[SC_ZE], sizeof (int) * (np + 1)));
+      }
+      qg_prob_args a = qg_prob_base_args (ctx, cfg, QG_REFS);
+      a.endvals = ctx->scratch[SC_ENDVALS].as<double> (); a.endex = ctx->scratch[SC_ENDEX].as<int> ();
+      a.store = ctx->scratch[SC_STORE].as<double> (); a.store_ex = ctx->scratch[SC_STOREEX].as<int> ();
+      a.rowacc = ctx->scratch[SC_ROWACC].as<double> ();
+      a.pair_zm = ctx->scratch[SC_ZM].as<double> (); a.pair_ze = ctx->scratch[SC_ZE].as<int> ();
+      a.seg_scal = ctx->scratch[SC_MISC1].as<double> ();
+      a.do_store = 1;
+      {
+        qg_timer tm (ctx, &ctx->stats.ms_forward);
+        QG_TRY (qg_launch_prob<0> (ctx, plan, a, ctx->scratch[SC_SEGS].as<qg_segment> ()));
+        QG_LAUNCH (qg_forward_prob_finalize_kernel, (unsigned) ((np + 63) / 64), 64, 0, ctx->stream,
+                   ctx->scratch[SC_PAIRDP].as<qg_pair_dp> (), (uint32_t) np, ctx->scratch[SC_MISC0].as<qg_segment> (),
+                   ctx->scratch[SC_ENDVALS].as<double> (), ctx->scratch[SC_ENDEX].as<int> (), ctx->scratch[SC_RS].as<double> (),
+                   ctx->scratch[SC_OUT0].as<double> (), ctx->scratch[SC_ZM].as<double> (), ctx->scratch[SC_ZE].as<int> ());
+        QG_TRY (qg_check_launch (ctx, "qg_forward_prob_finalize_kernel"));
+      }
+      {
+        qg_timer tm (ctx, &ctx->stats.ms_backward);
+        QG_TRY (qg_launch_prob<1> (ctx, plan, a, ctx->scratch[SC_SEGS].as<qg_segment> ()));
+        QG_LAUNCH (qg_backward_prob_finalize_kernel, (unsigned) ((np + 63) / 64), 64, 0, ctx->stream,
+                   ctx->scratch[SC_PAIRDP].as<qg_pair_dp> (), (uint32_t) np, ctx->scratch[SC_MISC0].as<qg_segment> (),
+                   ctx->scratch[SC_ENDVALS].as<double> (), ctx->scratch[SC_ENDEX].as<int> (), ctx->scratch[SC_RS].as<double> (),
+                   ctx->scratch[SC_OUT1].as<double> ());
+        QG_TRY (qg_check_launch (ctx, "qg_backward_prob_finalize_kernel"));
+      }
+    } else {
     qg_fill_args a = qg_base_args (ctx, cfg, QG_REFS);
     a.endvals = ctx->scratch[SC_ENDVALS].as<double> ();
     a.store = ctx->scratch[SC_STORE].as<double> ();
@@ -897,6 +1037,10 @@ extern "C" int qg_backward_counts (qg_ctx* ctx, const qg_dpconfig* cfg, size_t n
                  ctx->scratch[SC_PAIRDP].as<qg_pair_dp> (), (uint32_t) np, ctx->scratch[SC_MISC0].as<qg_segment> (),
                  ctx->scratch[SC_ENDVALS].as<double> (), ctx->d_lse.as<double> (), ctx->scratch[SC_OUT1].as<double> ());
       QG_TRY (qg_check_launch (ctx, "qg_backward_finalize_kernel"));
+    }
+    }
+    {
+      qg_timer tm (ctx, &ctx->stats.ms_backward);
       QG_LAUNCH (qg_counts_scatter_kernel, (unsigned) np, 256, 0, ctx->stream,
                  ctx->scratch[SC_PAIRDP].as<qg_pair_dp> (), ctx->scratch[SC_MISC0].as<qg_segment> (),
                  Y.d_tok.as<uint8_t> (), Y.d_qual.as<uint8_t> (), Y.d_off.as<uint64_t> (),
@@ -1068,13 +1212,16 @@ static int qg_overlap_ensure_table (qg_ctx* ctx, int strand, bool with_qual) {
 
 template<int DUMMY>
 static int qg_launch_overlap_fill (qg_ctx* ctx, const qg_dp_plan& plan, qg_ofill_args a, const qg_segment* d_segs_launch_order) {
+  QG_TRY (qg_fork (ctx));
+  int kcls = 0;
   for (const auto& L : plan.launches) {
+    cudaStream_t st; QG_TRY (qg_side (ctx, kcls++, &st));
     a.segs = d_segs_launch_order + L.begin;
     const bool multi = L.nw > 1;
     const unsigned block = 32u * L.nw;
 #define QG_CASE(RR) case RR: \
-      if (multi) { auto kfn = qg_overlap_fill_kernel<8, true>; QG_LAUNCH (kfn, L.count, block, 0, ctx->stream, a); } \
-      else { auto kfn = qg_overlap_fill_kernel<RR, false>; QG_LAUNCH (kfn, L.count, block, 0, ctx->stream, a); } break;
+      if (multi) { auto kfn = qg_overlap_fill_kernel<8, true>; QG_LAUNCH (kfn, L.count, block, 0, st, a); } \
+      else { auto kfn = qg_overlap_fill_kernel<RR, false>; QG_LAUNCH (kfn, L.count, block, 0, st, a); } break;
     switch (L.R) {
       QG_CASE (2) QG_CASE (3) QG_CASE (4) QG_CASE (5) QG_CASE (6) QG_CASE (7) QG_CASE (8)
       default: QG_FAIL (ctx, QG_ERR_INVALID, "internal: unsupported R=%d", L.R);
@@ -1082,6 +1229,7 @@ static int qg_launch_overlap_fill (qg_ctx* ctx, const qg_dp_plan& plan, qg_ofill
 #undef QG_CASE
     QG_TRY (qg_check_launch (ctx, "qg_overlap_fill_kernel"));
   }
+  QG_TRY (qg_join (ctx, kcls));
   return QG_OK;
 }
 

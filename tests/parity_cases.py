@@ -70,20 +70,35 @@ def check_viterbi(G, O, x, reads, s_or, cfg, xi, yi, use_quals=True):
     return v
 
 
-def check_forward(G, O, x, reads, s_or, cfg, xi, yi, use_quals=True):
-    """bit-exact (same table log-sum-exp, same fold order); the stated tolerance is 1e-3 nats per read"""
+FAST_LL_TOL = 1e-5      # nats per pair, probability-space kernels vs the reference's table log-sum-exp (stated bar: 1e-3)
+FAST_COUNT_RTOL = 1e-6  # stated bar: 1e-4 relative
+
+
+def check_forward(G, O, x, reads, s_or, cfg, xi, yi, use_quals=True, exact=True):
+    """exact=True: log-space kernels, bit-exact (same table log-sum-exp, same fold order).
+    exact=False: probability-space kernels, within FAST_LL_TOL nats (the stated tolerance is 1e-3 nats per read)"""
     xs, ys = seqbufs(x, reads, use_quals)
+    G.set_fb_exact(exact)
     f = G.forward(cfg, xi, yi)
     oc = oracle_cfg(cfg)
     for p, (a, b) in enumerate(zip(xi, yi)):
         o = O.forward(xs[a], ys[b], s_or, oc)
-        assert o["result"] == f[p] or (np.isinf(o["result"]) and np.isinf(f[p])), (p, o["result"], f[p])
+        if np.isinf(o["result"]):
+            assert np.isinf(f[p]) and f[p] < 0, (p, f[p])
+        elif exact:
+            assert o["result"] == f[p], (p, o["result"], f[p])
+        else:
+            assert abs(o["result"] - f[p]) <= FAST_LL_TOL, (p, o["result"], f[p])
     return f
 
 
-def check_backward(G, O, x, reads, s_or, cfg, xi, yi, rel=1e-9):
-    """counts within 1e-4 relative is the stated bar; we hold 1e-9 (only exp() differs)"""
+def check_backward(G, O, x, reads, s_or, cfg, xi, yi, rel=1e-9, exact=True):
+    """counts within 1e-4 relative is the stated bar; the log-space kernels hold 1e-9 (only exp() differs), the
+    probability-space kernels FAST_COUNT_RTOL"""
     xs, ys = seqbufs(x, reads)
+    G.set_fb_exact(exact)
+    if not exact:
+        return _check_backward_fast(G, O, xs, ys, s_or, cfg, xi, yi)
     r = G.backward_counts(cfg, xi, yi, per_pair=True)
     oc = oracle_cfg(cfg)
     tot = np.zeros_like(r["counts"])
@@ -98,20 +113,40 @@ def check_backward(G, O, x, reads, s_or, cfg, xi, yi, rel=1e-9):
     return r
 
 
-def check_estep(G, O, x, reads, s_or, nullp, cfg, use_null=True, n_iter=2, rel=1e-9):
+def check_estep(G, O, x, reads, s_or, nullp, cfg, use_null=True, n_iter=2, rel=1e-9, exact=True):
     """QuaffCountingTask::run replayed over `n_iter` E-steps (sortOrder pruning carried across)."""
     xs, ys = seqbufs(x, reads)
+    G.set_fb_exact(exact)
+    if not exact:
+        rel = FAST_COUNT_RTOL
     null_ll = np.array([api.null_loglike(nullp, r, G.L) for r in reads])
     so_g = so_o = None
     for it in range(n_iter):
         g = G.estep(cfg, use_null, null_ll, so_g)
         o = O.estep(xs, ys, s_or, nullp, use_null, oracle_cfg(cfg), so_o)
-        np.testing.assert_allclose(g["y_loglike"], o["loglike"], rtol=1e-12)
+        np.testing.assert_allclose(g["y_loglike"], o["loglike"], rtol=1e-12 if exact else 0, atol=0 if exact else FAST_LL_TOL)
         assert g["sort_order"] == o["sort_order"], (it, g["sort_order"], o["sort_order"])
-        np.testing.assert_allclose(g["counts"], o["counts"], rtol=rel, atol=1e-12)
+        np.testing.assert_allclose(g["counts"], o["counts"], rtol=rel, atol=1e-12 if exact else 1e-9 * max(1.0, float(np.abs(o["counts"]).max())))
         assert abs(g["loglike"] - o["loglike"].sum()) <= 1e-9 * abs(g["loglike"])
         so_g, so_o = g["sort_order"], o["sort_order"]
     return g
+
+
+def _check_backward_fast(G, O, xs, ys, s_or, cfg, xi, yi):
+    r = G.backward_counts(cfg, xi, yi, per_pair=True)
+    oc = oracle_cfg(cfg)
+    tot = np.zeros_like(r["counts"])
+    for p, (a, b) in enumerate(zip(xi, yi)):
+        o = O.backward(xs[a], ys[b], s_or, oc)
+        if not np.isfinite(o["fwd"]):
+            assert np.isinf(r["fwd"][p])
+            continue
+        assert abs(o["fwd"] - r["fwd"][p]) <= FAST_LL_TOL and abs(o["back"] - r["back"][p]) <= FAST_LL_TOL, (p, o["fwd"], r["fwd"][p], o["back"], r["back"][p])
+        scale = max(1.0, float(np.abs(o["counts"]).max()))
+        np.testing.assert_allclose(r["counts_per_pair"][p], o["counts"], rtol=FAST_COUNT_RTOL, atol=1e-9 * scale)
+        tot += o["counts"]
+    np.testing.assert_allclose(r["counts"], tot, rtol=FAST_COUNT_RTOL, atol=1e-9 * max(1.0, float(np.abs(tot).max())))
+    return r
 
 
 def overlap_pairs(n_originals, n_total):

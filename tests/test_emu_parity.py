@@ -89,3 +89,17 @@ def test_emu_overlap(emu, oracle):
     emu.set_reads(seqs); emu.set_overlap_params(qp)
     r, nf = pc.check_overlap(emu, oracle, seqs, len(reads), qp, api.dp_config(kmer_threshold=5))
     assert nf > 0
+
+
+def test_emu_probability_space_forward_backward(emu, oracle, workload):
+    """the fast (default) train kernels: probability space, block-floating exponents"""
+    import os
+    from quaff_b200.params import QuaffNullParams
+    x, reads, s_or = workload
+    xi, yi = pc.all_pairs(len(x), len(reads))
+    cfg = api.dp_config(kmer_threshold=6)
+    pc.check_forward(emu, oracle, x, reads, s_or, cfg, xi, yi, exact=False)
+    pc.check_backward(emu, oracle, x, reads, s_or, cfg, xi, yi, exact=False)
+    nullp = QuaffNullParams.load(os.path.join(os.path.dirname(__file__), "golden", "testquaffnullparams.json"))
+    pc.check_estep(emu, oracle, x, reads, s_or, nullp, cfg, use_null=True, n_iter=1, exact=False)
+    emu.set_fb_exact(True)

@@ -22,6 +22,7 @@ def test_gpu_matches_reference_vectors(gpu, name):
     cfg = api.dp_config(**meta["cfg"])
     use_quals = all(r.has_qual() for r in reads)
     gpu.set_refs(x); gpu.set_reads(reads, use_quals=use_quals); gpu.set_params(qp)
+    gpu.set_fb_exact(True)                      # the log-space kernels: Forward is bit-exact against the reference vectors
     xi = np.array([r["x"] for r in meta["pairs"]], np.uint32); yi = np.array([r["y"] for r in meta["pairs"]], np.uint32)
     env24, cu = gpu.envelopes(cfg, xi, yi, cell_size=24)
     env48, _ = gpu.envelopes(cfg, xi, yi, cell_size=48)
@@ -79,6 +80,7 @@ def test_gpu_reference_own_golden_files(gpu):
     assert null_ll == g["null_loglike"]
     cfg = api.dp_config(kmer_threshold=-1, max_size=g["max_size"])
     gpu.set_refs([c8]); gpu.set_reads([c8]); gpu.set_params(qp)
+    gpu.set_fb_exact(True)
     env, _ = gpu.envelopes(cfg, [0], [0])
     assert list(env[0]) == [0]
     a = gpu.align_reads(cfg, np.array([null_ll]))

@@ -127,3 +127,31 @@ def test_overlap(gpu, oracle):
     r, nf = pc.check_overlap(gpu, oracle, seqs, len(reads), qp, api.dp_config(kmer_threshold=14))
     assert nf >= 5
     r, nf = pc.check_overlap(gpu, oracle, seqs, len(reads), qp, api.dp_config(kmer_threshold=14), use_quals=True)
+
+
+def test_probability_space_forward_backward(gpu, oracle, workload):
+    """the default train kernels (probability space, reference-compatible log-sum-exp cut-off) against the oracle:
+    Forward within 1e-5 nats (bar 1e-3), counts within 1e-6 relative (bar 1e-4), same gate / sortOrder decisions"""
+    import os
+    from quaff_b200.params import QuaffNullParams
+    x, reads, s_or = workload
+    xi, yi = pc.all_pairs(len(x), len(reads))
+    cfg = api.dp_config(kmer_threshold=20)
+    pc.check_forward(gpu, oracle, x, reads, s_or, cfg, xi, yi, exact=False)
+    pc.check_backward(gpu, oracle, x, reads, s_or, cfg, xi, yi, exact=False)
+    nullp = QuaffNullParams.load(os.path.join(os.path.dirname(__file__), "golden", "testquaffnullparams.json"))
+    pc.check_estep(gpu, oracle, x, reads, s_or, nullp, cfg, use_null=True, n_iter=2, exact=False)
+    gpu.set_fb_exact(True)
+
+
+def test_probability_space_order2_and_global(gpu, oracle):
+    from quaff_b200.params import random_params
+    x, reads = pc.make_workload(ref_len=20000, n_reads=3, read_len=1500, seed=7)
+    qp = random_params(np.random.default_rng(5), match_k=3, gap_k=2)
+    gpu.set_refs(x); gpu.set_reads(reads); gpu.set_params(qp)
+    s_or = oracle.scores(qp)
+    xi, yi = pc.all_pairs(len(x), len(reads))
+    for cfg in (api.dp_config(kmer_threshold=14), api.dp_config(kmer_threshold=14, local=False)):
+        pc.check_forward(gpu, oracle, x, reads, s_or, cfg, xi, yi, exact=False)
+        pc.check_backward(gpu, oracle, x, reads, s_or, cfg, xi, yi, exact=False)
+    gpu.set_fb_exact(True)
