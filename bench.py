@@ -184,6 +184,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the Forward/Backward side measurement")
     ap.add_argument("--ref-all-steps", action="store_true")
+    ap.add_argument("--contexts", type=int, default=2, help="contexts (host thread + stream each) per GPU")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl != "reference":
         args.warmup = max(args.warmup, 3) if os.environ.get("QB_ALLOW_SHORT_WARMUP") is None else args.warmup
@@ -210,8 +211,9 @@ def main():
     B = args.reads_per_step
     x, batches = make_workload(rank, POOL_BATCHES, B, args.ref_len, args.read_len)
     qp, nullp = load_models()
-    G = api.QuaffGPU(device=local)
-    G.set_refs(x); G.set_params(qp)
+    P = api.QuaffGPUPool(device=local, n_ctx=args.contexts)
+    G = P.ctxs[0]
+    P.set_refs(x); P.set_params(qp)
     cfg = api.dp_config(kmer_threshold=20, band_size=64, kmer_len=6)
     flat = [api._flatten(b, True) for b in batches]
     null_ll = [np.array([api.null_loglike(nullp, r, G.L) for r in b]) for b in batches]
@@ -222,40 +224,43 @@ def main():
         pinned.append((pt.numpy(), pq.numpy(), off))
 
     # ---- resident-input arm: all pool batches live on the device as one READS set --------------------------------
-    all_reads = [r for b in batches for r in b]
-    G.set_reads(all_reads)
-    all_null = np.concatenate(null_ll)
+    P.set_read_batches(flat)
 
     def resident_step(i):
         b = i % POOL_BATCHES
-        return G.align_reads(cfg, all_null[b * B:(b + 1) * B], first=b * B, count=B, split_paths=False)
+        return P.align_batch(cfg, b, null_ll[b])
+
+    def pool_stats(reset=False):
+        sts = P.stats(reset)
+        out = {k: (sum(s[k] for s in sts) if not k.startswith("ms_") else max(s[k] for s in sts)) for k in sts[0]}
+        out["ms_sum"] = {k: sum(s[k] for s in sts) for k in sts[0] if k.startswith("ms_")}
+        return out
 
     for i in range(args.warmup):
         resident_step(i)
     sampler = ClockSampler(local); sampler.start()
-    G.stats(reset=True)
+    pool_stats(reset=True)
     barrier(); t0 = time.perf_counter()
     for i in range(args.steps):
         out = resident_step(args.warmup + i)
     barrier(); t1 = time.perf_counter()
-    st = G.stats()
+    st_timed = pool_stats()
     dt = t1 - t0
     # ---- e2e arm: host buffers in, host results out, every step ---------------------------------------------------
     def e2e_step(i):
         b = i % POOL_BATCHES
         tok, qual, off = pinned[b]
-        G.set_seqs_raw(api.QG_READS, tok, qual, off)
-        r = G.align_reads(cfg, null_ll[b], split_paths=False)
-        return r
+        P.set_reads_raw(tok, qual, off)
+        return P.align_reads(cfg, null_ll[b])
 
     for i in range(args.warmup):
         e2e_step(i)
-    G.stats(reset=True)
+    pool_stats(reset=True)
     barrier(); t2 = time.perf_counter()
     for i in range(args.steps):
         r = e2e_step(args.warmup + i)
     barrier(); t3 = time.perf_counter()
-    st_e = G.stats()
+    st_e = pool_stats()
     clocks = sampler.stop()
     dt_e = t3 - t2
     h2d = int(pinned[0][0].nbytes + pinned[0][1].nbytes + pinned[0][2].nbytes)
@@ -280,10 +285,22 @@ def main():
                  "fwd_bwd_gcups": 2 * cu_b / 1e9 / ((s2["ms_forward"] + s2["ms_backward"]) / 1e3),
                  "formulation": "FP64 probability space with the reference's log-sum-exp cut-off (default); the bit-exact log-space kernels are selectable (QG_OPT_FB_EXACT)"}
 
+    # ---- kernel figures for the roofline: ONE context alone (the timed regions interleave several contexts on the GPU, so
+    # their per-stream event times include interference), one step's share of the reads, CUDA events on the launching stream
+    P.set_read_batches(flat)
+    first, count, lo, hi = P.batch_ranges[0][0]
+    G.align_reads(cfg, null_ll[0][lo:hi], first=first, count=count, split_paths=False)
+    G.stats(reset=True)
+    n_iso = 2
+    for _ in range(n_iso):
+        G.align_reads(cfg, null_ll[0][lo:hi], first=first, count=count, split_paths=False)
+    st = G.stats()
+    iso_reads = count * n_iso
+
     # ---- reduce over ranks: the slowest rank defines the step -----------------------------------------------------
     times = torch.tensor([dt, dt_e], dtype=torch.float64, device="cuda")
     sums = torch.tensor([float(st["cell_updates"]), float(st["kmer_hits"]), st["ms_seed"], st["ms_viterbi"], st["ms_traceback"],
-                         float(st["kernel_launches"]), float(st["trace_bytes"])], dtype=torch.float64, device="cuda")
+                         float(st_timed["kernel_launches"]), float(st["trace_bytes"])], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
         stage_max = sums.clone(); dist.all_reduce(stage_max, op=dist.ReduceOp.MAX)
@@ -300,13 +317,13 @@ def main():
         ms_seed, ms_vit, ms_tb = float(stage_max[2]), float(stage_max[3]), float(stage_max[4])
         launches = int(float(sums[5]) / world)
         hbm_peak, peak_src = measured_peaks()
-        cu_rank = cu_total / world; hits_rank = hits_total / world
+        cu_rank = cu_total / world; hits_rank = hits_total / world        # of the isolated pass (iso_reads reads)
         vit_cups = cu_rank / (ms_vit / 1e3); seed_hps = hits_rank / (ms_seed / 1e3)
         # dominant kernel by device time
         seed_dom = ms_seed >= ms_vit
         # algorithmic HBM bytes: seeding streams the 2 B/position k-mer codes of the reference once per (read, strand,
         # chunk overlap) ; the Viterbi fill writes 4 B of pointers per lane and macro-step (= trace_bytes)
-        seed_bytes = 2.0 * (args.ref_len * 2) * B * args.steps
+        seed_bytes = 2.0 * (args.ref_len * 2) * iso_reads
         vit_bytes = float(sums[6]) / world
         roofline = {
             "kernel": "qg_seed_kernel" if seed_dom else "qg_fill_kernel<R,Viterbi>",
@@ -323,7 +340,8 @@ def main():
             "all": {"seed_ghits_s": seed_hps / 1e9, "seed_frac_of_smem_atomic_peak": seed_hps / PEAK_SMEM_ATOMIC,
                     "viterbi_gcups": vit_cups / 1e9, "viterbi_frac_of_fp32_roofline": vit_cups / (PEAK_LANE_INSTR / INSTR_PER_CU["viterbi"]),
                     "viterbi_frac_of_fp64_roofline": vit_cups / (PEAK_LANE_INSTR / 2 / INSTR_PER_CU["viterbi"]),
-                    "ms_per_step": {"seed": ms_seed / args.steps, "viterbi_fill": ms_vit / args.steps, "traceback": ms_tb / args.steps}},
+                    "isolated_pass": {"reads": iso_reads, "ms_seed": ms_seed, "ms_viterbi_fill": ms_vit, "ms_traceback": ms_tb,
+                                      "note": "one context alone after the timed regions; kernel times by CUDA events on its stream"}},
         }
         if train:
             roofline["all"]["forward_gcups"] = train["forward_gcups"]; roofline["all"]["backward_gcups"] = train["backward_gcups"]
@@ -343,20 +361,20 @@ def main():
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": "cfg4: quaff align, synthetic 8 kb nanopore-like reads (12% error) vs 5 Mb random reference, both strands, "
                                    "-kmatch 6 -kmatchn 20 -kmatchband 64, default params, fixed null model",
-                       "reads_per_step_per_gpu": B, "ref_len": args.ref_len, "read_len": args.read_len,
+                       "reads_per_step_per_gpu": B, "ref_len": args.ref_len, "read_len": args.read_len, "contexts_per_gpu": args.contexts,
                        "sharding": "reads over ranks, reference replicated, no collective on the align path",
                        "l2": "inputs larger than L2: every step writes and re-reads its own ~%.1f GB of traceback pointers and alternates between %d read batches"
-                             % (float(sums[6]) / world / args.steps / 1e9, POOL_BATCHES)},
+                             % (float(sums[6]) / world / iso_reads * B / 1e9, POOL_BATCHES)},
             "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": dt_e / args.steps * 1e3},
             "gpu_launches": launches,
             "clocks": clocks,
-            "gcups": {"viterbi_fill": vit_cups / 1e9, "cell_updates_per_read": cu_rank / (B * args.steps), "kmer_hits_per_read": hits_rank / (B * args.steps)},
+            "gcups": {"viterbi_fill": vit_cups / 1e9, "cell_updates_per_read": cu_rank / iso_reads, "kmer_hits_per_read": hits_rank / iso_reads},
             "roofline": roofline,
             "cpu_baseline": cpu,
             "train": train,
         }
         print(json.dumps(line), flush=True)
-    G.close()
+    P.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -344,3 +344,119 @@ class QuaffGPU:
         st = Stats()
         self._check(self.L.qg_get_stats(self.ctx, C.byref(st), int(reset)))
         return st.as_dict()
+
+
+class QuaffGPUPool:
+    """Several contexts on ONE GPU, driven by one host thread each.  Every context owns a stream and its scratch, so the
+    host-side work of one (pair lists, plans, result copies) and its kernels overlap with the kernels of the others: the
+    seeding kernel (shared-memory atomics) and the DP fills (FP64 issue) share an SM well.  Reads are split contiguously
+    over the contexts; the reference and the model are replicated (a few tens of MB)."""
+
+    def __init__(self, device: int = 0, n_ctx: int = 2, lib_path: Optional[str] = None):
+        from concurrent.futures import ThreadPoolExecutor
+        self.ctxs = [QuaffGPU(device=device, lib_path=lib_path) for _ in range(n_ctx)]
+        self.pool = ThreadPoolExecutor(max_workers=n_ctx)
+        self.bounds: List[Tuple[int, int]] = []
+
+    @property
+    def L(self):
+        return self.ctxs[0].L
+
+    def close(self):
+        self.pool.shutdown(wait=True)
+        for g in self.ctxs:
+            g.close()
+
+    def _each(self, fn):
+        return [f.result() for f in [self.pool.submit(fn, k, g) for k, g in enumerate(self.ctxs)]]
+
+    def set_refs(self, refs):
+        self._each(lambda k, g: g.set_refs(refs))
+
+    def set_params(self, qp):
+        s = scores_from_params(qp, self.L)
+        self._each(lambda k, g: g.set_align_scores(s))
+
+    def _split(self, n: int):
+        w = len(self.ctxs)
+        base, extra = divmod(n, w)
+        self.bounds = []
+        lo = 0
+        for k in range(w):
+            hi = lo + base + (1 if k < extra else 0)
+            self.bounds.append((lo, hi)); lo = hi
+
+    def set_reads_raw(self, tok: np.ndarray, qual: Optional[np.ndarray], off: np.ndarray):
+        """host buffers -> each context uploads its contiguous share of the reads"""
+        n = len(off) - 1
+        self._split(n)
+
+        def up(k, g):
+            lo, hi = self.bounds[k]
+            o = off[lo:hi + 1]
+            b0, b1 = int(o[0]), int(o[-1])
+            g.set_seqs_raw(QG_READS, tok[b0:b1], None if qual is None else qual[b0:b1], o - o[0])
+        self._each(up)
+
+    def set_reads(self, reads, use_quals: bool = True):
+        want = use_quals and all(r.has_qual() for r in reads) and len(reads) > 0
+        tok, qual, off = _flatten(reads, want)
+        self.set_reads_raw(tok, qual, off)
+
+    def set_read_batches(self, batches):
+        """batches: list of (tok, qual, off) host arrays.  Every context receives its contiguous share of EVERY batch, laid
+        out batch after batch, so that a later align_batch(b) only touches resident data."""
+        w = len(self.ctxs)
+        self.batch_ranges = []            # [batch][ctx] -> (first read in the context's set, count, global lo, global hi)
+        per_ctx = [([], [], [np.zeros(1, dtype=np.uint64)]) for _ in range(w)]
+        counts = [0] * w
+        for tok, qual, off in batches:
+            n = len(off) - 1
+            base, extra = divmod(n, w)
+            lo = 0; row = []
+            for k in range(w):
+                hi = lo + base + (1 if k < extra else 0)
+                o = off[lo:hi + 1]; b0, b1 = int(o[0]), int(o[-1])
+                t, q, offs = per_ctx[k]
+                t.append(tok[b0:b1])
+                if qual is not None:
+                    q.append(qual[b0:b1])
+                offs.append(o[1:] - o[0] + offs[-1][-1])
+                row.append((counts[k], hi - lo, lo, hi)); counts[k] += hi - lo
+                lo = hi
+            self.batch_ranges.append(row)
+
+        def up(k, g):
+            t, q, offs = per_ctx[k]
+            g.set_seqs_raw(QG_READS, np.concatenate(t), np.concatenate(q) if q else None, np.concatenate(offs))
+        self._each(up)
+
+    def _merge(self, parts):
+        out = {k: np.concatenate([p[k] for p in parts]) for k in ("best_ref", "score", "x_start", "x_end", "paths")}
+        base = np.uint64(0); cat = []
+        for p in parts:
+            o = np.asarray(p["path_offsets"], dtype=np.uint64)
+            cat.append(o[:-1] + base); base = base + o[-1]
+        out["path_offsets"] = np.concatenate(cat + [np.array([base], dtype=np.uint64)])
+        return out
+
+    def align_batch(self, cfg: DPConfig, b: int, null_ll: np.ndarray):
+        """seam A over resident batch b (see set_read_batches); null_ll is the batch's, in read order"""
+        null_ll = np.ascontiguousarray(null_ll, dtype=np.float64)
+
+        def run(k, g):
+            first, count, lo, hi = self.batch_ranges[b][k]
+            return g.align_reads(cfg, null_ll[lo:hi], first=first, count=count, split_paths=False)
+        return self._merge(self._each(run))
+
+    def align_reads(self, cfg: DPConfig, null_ll: np.ndarray):
+        """seam A over everything uploaded with set_reads / set_reads_raw"""
+        null_ll = np.ascontiguousarray(null_ll, dtype=np.float64)
+
+        def run(k, g):
+            lo, hi = self.bounds[k]
+            return g.align_reads(cfg, null_ll[lo:hi], split_paths=False)
+        return self._merge(self._each(run))
+
+    def stats(self, reset: bool = False) -> List[dict]:
+        return [g.stats(reset) for g in self.ctxs]

@@ -170,11 +170,13 @@ qg_fill_kernel (const qg_fill_args a) {
   uint64_t win = 0; int pw = 0; bool have_win = false;
 
   const int total = ylen + 32 * NW - 1;
+  // row parameters are fetched one macro-step ahead: the 64 B load of row j+1 is in flight while row j is computed
+  qg_rowp Pnext = rp[(1 - vl) < 0 ? 0 : (1 - vl)];
   for (int u = 1; u <= total; ++u) {
     const int j = u - vl;
     const bool active = (j >= 1) && (j <= ylen);
-    const int jj = j < 0 ? 0 : (j > ylen + 1 ? ylen + 1 : j);
-    const qg_rowp P = rp[jj];
+    const qg_rowp P = Pnext;
+    { const int jn = j + 1; Pnext = rp[jn < 0 ? 0 : (jn > ylen + 1 ? ylen + 1 : jn)]; }
     const int p0 = d0 + j - 1;                              // x index (0-based) of cell 0: i - 1
     if (active && (!have_win || p0 < pw || p0 + R > pw + 32)) { win = qg_fetch32 (xw, nxw, p0); pw = p0; have_win = true; }
     const uint64_t wsh = win >> (2 * ((p0 - pw) & 31));
@@ -366,6 +368,93 @@ __global__ void qg_traceback_kernel (const qg_pair_dp* __restrict__ pairs, uint3
   }
   x_start[p] = (uint32_t) (i + 1);
   path_len[p] = n;
+}
+
+// Warp-cooperative traceback for single-warp segments: the pointer words of 32 consecutive macro-steps (32 x 128 B,
+// each row one coalesced load) are staged in shared memory, then lane 0 walks inside the tile.  A step never increases
+// the macro-step index u = j + lane-of-slot and lowers it by at most one, so a tile serves >= 32 steps: one DRAM
+// round trip per 32+ steps instead of one per step.
+#define QG_TB_WARPS 4
+__global__ void __launch_bounds__ (32 * QG_TB_WARPS)
+qg_traceback_warp_kernel (const qg_pair_dp* __restrict__ pairs, uint32_t npairs, const qg_segment* __restrict__ segs,
+                          const uint32_t* __restrict__ trace, const double* __restrict__ score, const uint32_t* __restrict__ x_end,
+                          uint32_t* __restrict__ x_start, uint8_t* __restrict__ path_scratch, uint32_t* __restrict__ path_len,
+                          uint32_t* __restrict__ err_flag) {
+  __shared__ uint32_t s_tile[QG_TB_WARPS][32][33];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const uint32_t p = blockIdx.x * QG_TB_WARPS + w;
+  const bool have = p < npairs;
+  const qg_pair_dp pd = pairs[have ? p : 0];
+  bool go = have && pd.want_path && (score[have ? p : 0] > QG_NEG_INF);
+  if (have && lane == 0) { x_start[p] = 0; path_len[p] = 0; }
+  int i = go ? (int) x_end[p] : 0, j = (int) pd.ylen, state = go ? 1 : 0;
+  uint32_t n = 0, cs = pd.seg_begin;
+  uint8_t* buf = path_scratch + pd.path_off;
+  int fail = 0;
+  while (__shfl_sync (QG_FULL_MASK, (int) (state != 0 && !fail), 0)) {
+    // lane 0 walks and decides the segment and the tile; everybody follows
+    qg_segment sg = segs[cs];
+    if (lane == 0 && state != 0 && !fail) {
+      const int d = i - j;
+      if (d < sg.dlo || d >= sg.dlo + (int) sg.width) {
+        bool found = false;
+        for (uint32_t s = pd.seg_begin; s < pd.seg_end; ++s) {
+          const qg_segment t = segs[s];
+          if (d >= t.dlo && d < t.dlo + (int) t.width) { cs = s; found = true; break; }
+        }
+        if (!found) fail = 1;
+      }
+    }
+    cs = __shfl_sync (QG_FULL_MASK, cs, 0);
+    sg = segs[cs];
+    const int R = (int) sg.R;
+    int u_top = 0;
+    if (lane == 0 && state != 0 && !fail) u_top = j + (i - j - sg.dlo) / R;
+    u_top = __shfl_sync (QG_FULL_MASK, u_top, 0);
+    const bool multi = sg.nwarps > 1;
+    if (!multi) {
+#pragma unroll 8
+      for (int r = 0; r < 32; ++r) {
+        const int u = u_top - r;
+        s_tile[w][r][lane] = (u >= 0) ? trace[sg.trace_off + (uint64_t) u * 32 + lane] : 0u;
+      }
+    }
+    __syncwarp ();
+    if (lane == 0 && state != 0 && !fail) {
+      while (state != 0) {
+        const int d = i - j;
+        const int slot = d - sg.dlo;
+        if (slot < 0 || slot >= (int) sg.width) { fail = 1; break; }       // cannot happen: paths do not cross the halo
+        const int vl = slot / R, c = slot - vl * R;
+        const int u = j + vl;
+        uint32_t word;
+        if (multi) word = trace[sg.trace_off + (uint64_t) u * (32 * sg.nwarps) + vl];
+        else {
+          if (u < u_top - 31) break;                                       // next tile
+          word = s_tile[w][u_top - u][vl];
+        }
+        const uint32_t nib = (word >> (4 * c)) & 15u;
+        if (n >= pd.path_cap) { fail = 2; break; }
+        if (state == 1) {
+          buf[pd.path_cap - 1 - n] = QG_OP_MATCH; ++n; --i; --j;
+          const uint32_t src = nib & 3u;
+          state = (src == 0) ? 1 : (src == 1) ? 2 : (src == 2) ? 3 : 0;
+        } else if (state == 2) {
+          buf[pd.path_cap - 1 - n] = QG_OP_INSERT; ++n; --j;
+          state = (nib & 4u) ? 2 : 1;
+        } else {
+          buf[pd.path_cap - 1 - n] = QG_OP_DELETE; ++n; --i;
+          state = (nib & 8u) ? 3 : 1;
+        }
+        if (i < 0 || j < 0) { fail = 3; break; }
+      }
+    }
+    __syncwarp ();
+  }
+  if (have && lane == 0) {
+    if (fail) *err_flag = (uint32_t) fail;
+    if (go) { x_start[p] = (uint32_t) (i + 1); path_len[p] = n; }
+  }
 }
 
 // gather the back-to-front scratch paths into one contiguous 5'->3' array

@@ -112,11 +112,12 @@ qg_forward_prob_kernel (const qg_prob_args a) {
   uint64_t win = 0; int pw = 0; bool have_win = false;
 
   const int total = ylen + 31;
+  qg_rowq Pnext = rq[(1 - lane) < 0 ? 0 : (1 - lane)];     // fetched one macro-step ahead
   for (int u = 1; u <= total; ++u) {
     const int j = u - lane;
     const bool active = (j >= 1) && (j <= ylen);
-    const int jj = j < 0 ? 0 : (j > ylen + 1 ? ylen + 1 : j);
-    const qg_rowq P = rq[jj];
+    const qg_rowq P = Pnext;
+    { const int jn = j + 1; Pnext = rq[jn < 0 ? 0 : (jn > ylen + 1 ? ylen + 1 : jn)]; }
     const int p0 = d0 + j - 1;
     if (active && (!have_win || p0 < pw || p0 + R > pw + 32)) { win = qg_fetch32 (xw, nxw, p0); pw = p0; have_win = true; }
     const uint64_t wsh = win >> (2 * ((p0 - pw) & 31));

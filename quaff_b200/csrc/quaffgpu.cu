@@ -693,7 +693,7 @@ static int qg_viterbi_impl (qg_ctx* ctx, const qg_dpconfig* cfg, size_t n_pairs,
         QG_TRY (qg_upload (ctx, ctx->scratch[SC_PAIRDP], plan.pairs.data (), sizeof (qg_pair_dp) * np));
         QG_TRY (qg_reserve (ctx, ctx->scratch[SC_PATHSCR], scratch_bytes + 16));
         QG_CUDA (ctx, cudaMemsetAsync (ctx->scratch[SC_FLAGS].p, 0, 64, ctx->stream));
-        QG_LAUNCH (qg_traceback_kernel, (unsigned) ((np + 63) / 64), 64, 0, ctx->stream,
+        QG_LAUNCH (qg_traceback_warp_kernel, (unsigned) ((np + QG_TB_WARPS - 1) / QG_TB_WARPS), 32 * QG_TB_WARPS, 0, ctx->stream,
                    ctx->scratch[SC_PAIRDP].as<qg_pair_dp> (), (uint32_t) np, ctx->scratch[SC_MISC0].as<qg_segment> (),
                    ctx->scratch[SC_TRACE].as<uint32_t> (), ctx->scratch[SC_OUT0].as<double> (), ctx->scratch[SC_OUT2].as<uint32_t> (),
                    ctx->scratch[SC_OUT1].as<uint32_t> (), ctx->scratch[SC_PATHSCR].as<uint8_t> (), ctx->scratch[SC_OUT3].as<uint32_t> (),
