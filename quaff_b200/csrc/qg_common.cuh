@@ -118,6 +118,8 @@ struct qg_ctx {
   // scratch, grown on demand and reused across calls
   qg_dbuf scratch[40];
   int fb_exact = 0;                  // QG_OPT_FB_EXACT
+  void* h_pinned = nullptr;          // pinned staging for large device-to-host copies
+  size_t h_pinned_cap = 0;
 };
 
 static inline int qg_reserve (qg_ctx* ctx, qg_dbuf& b, size_t bytes) {

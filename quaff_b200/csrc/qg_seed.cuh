@@ -91,7 +91,6 @@ qg_seed_kernel (const qg_seed_item* __restrict__ items, const qg_pair_desc* __re
   __shared__ uint32_t s_warp_tot[QG_SEED_THREADS / 32];
   __shared__ int s_open_lo, s_open_hi, s_have_open;
   __shared__ uint32_t s_nruns;
-  __shared__ int s_any, s_hotmax;                            // s_hotmax: largest diagonal whose counter has reached the threshold
 
   const qg_seed_item it = items[blockIdx.x];
   const qg_pair_desc pd = pairs[it.pair];
@@ -104,7 +103,7 @@ qg_seed_kernel (const qg_seed_item* __restrict__ items, const qg_pair_desc* __re
 
   // -- 1. bucket index of the read: counting sort of k-mer start positions by k-mer code
   for (uint32_t c = tid; c < ring; c += QG_SEED_THREADS) cnt[c] = 0;
-  if (tid == 0) { s_have_open = 0; s_nruns = 0; s_open_lo = 0; s_open_hi = 0; s_any = 0; s_hotmax = -2147483647 - 1; }
+  if (tid == 0) { s_have_open = 0; s_nruns = 0; s_open_lo = 0; s_open_hi = 0; }
   __syncthreads ();
   for (int j = tid; j < nyk; j += QG_SEED_THREADS) atomicAdd (&cnt[yc[j]], 1u);
   __syncthreads ();
@@ -136,8 +135,6 @@ qg_seed_kernel (const qg_seed_item* __restrict__ items, const qg_pair_desc* __re
   int i_last = d_end - 1 + span;                          // inclusive
   if (i_last > xlen - k) i_last = xlen - k;
   const int min_diag = 1 - ylen, max_diag = xlen - 1;
-  const bool always_scan = COUNTS || threshold <= 1;
-  const uint32_t thr_m1 = (uint32_t) (threshold - 1);
   const uint32_t dlen = (uint32_t) (d_end - d_begin);
   int emit_lo = d_begin;
   uint32_t my_hits = 0;
@@ -148,7 +145,6 @@ qg_seed_kernel (const qg_seed_item* __restrict__ items, const qg_pair_desc* __re
     uint32_t code[QG_SEED_PPT];
 #pragma unroll
     for (int r = 0; r < QG_SEED_PPT; ++r) { const int i = i0 + r * QG_SEED_THREADS + tid; code[r] = (i < i1) ? (uint32_t) xc[i] : 0xFFFFu; }
-    int hotd = -2147483647 - 1;
 #pragma unroll
     for (int r = 0; r < QG_SEED_PPT; ++r) {
       if (code[r] != 0xFFFFu) {
@@ -157,59 +153,62 @@ qg_seed_kernel (const qg_seed_item* __restrict__ items, const qg_pair_desc* __re
         const uint16_t* bp = bpos + (e >> 16);
         const uint32_t len = e & 0xFFFFu;
         if (i >= d_begin + span && i < d_end) {           // every diagonal this position can hit belongs to the item
-          for (uint32_t t = 0; t < len; ++t) {
-            const int sd = i + (int) bp[t];                 // d + yLen
-            const uint32_t old = atomicAdd (&cnt[(uint32_t) sd & mask], 1u);
-            if (old == thr_m1 && sd - ylen > hotd) hotd = sd - ylen;
-          }
+          // bucket lengths are Poisson(~2): the first four entries are predicated straight-line code (no loop
+          // bookkeeping, no divergence among lanes with different lengths), the rare longer tails loop
+          if (len > 0) atomicAdd (&cnt[(uint32_t) (i + (int) bp[0]) & mask], 1u);
+          if (len > 1) atomicAdd (&cnt[(uint32_t) (i + (int) bp[1]) & mask], 1u);
+          if (len > 2) atomicAdd (&cnt[(uint32_t) (i + (int) bp[2]) & mask], 1u);
+          if (len > 3) atomicAdd (&cnt[(uint32_t) (i + (int) bp[3]) & mask], 1u);
+          for (uint32_t t = 4; t < len; ++t) atomicAdd (&cnt[(uint32_t) (i + (int) bp[t]) & mask], 1u);
           my_hits += len;
         } else {
           const uint32_t ib = (uint32_t) (i - ylen - d_begin);     // d - d_begin = ib + bp[t]
           for (uint32_t t = 0; t < len; ++t) {
             const uint32_t v = bp[t];
-            if (ib + v < dlen) {
-              const int sd = i + (int) v;
-              const uint32_t old = atomicAdd (&cnt[(uint32_t) sd & mask], 1u);
-              if (old == thr_m1 && sd - ylen > hotd) hotd = sd - ylen;
-              ++my_hits;
-            }
+            if (ib + v < dlen) { atomicAdd (&cnt[(uint32_t) (i + (int) v) & mask], 1u); ++my_hits; }
           }
         }
       }
     }
-    if (hotd != -2147483647 - 1) atomicMax (&s_hotmax, hotd);
     if (my_hits > 0x40000000u) { my_hits64 += my_hits; my_hits = 0; }
     __syncthreads ();
     // diagonals below i1 - span can receive no further hits
     int emit_hi = (i1 > i_last) ? d_end : i1 - span;
     if (emit_hi > d_end) emit_hi = d_end;
     if (emit_hi > emit_lo) {
-      if (always_scan || s_hotmax >= emit_lo) {         // a diagonal at or beyond emit_lo has reached the threshold
-        const int ngroups = (emit_hi - emit_lo + 31) / 32;
-        for (int g0 = 0; g0 < ngroups; g0 += QG_SEED_STEP / 32) {
-          const int gcount = (ngroups - g0 < QG_SEED_STEP / 32) ? ngroups - g0 : QG_SEED_STEP / 32;
-          for (int g = wid; g < gcount; g += QG_SEED_THREADS / 32) {
-            const int d = emit_lo + (g0 + g) * 32 + lane;
-            uint32_t c = 0;
-            if (d < emit_hi) {
-              const uint32_t idx = (uint32_t) (d + ylen) & mask; c = cnt[idx]; cnt[idx] = 0;
-              if (COUNTS) { counts_out[pd.count_off + (uint64_t) (d + span)] = c; c = 0; }      // memory-guided mode: raw counts only
-            }
-            const uint32_t m = __ballot_sync (QG_FULL_MASK, d < emit_hi && (int) c >= threshold && c > 0);
-            if (lane == 0) { seedmask[g] = m; if (m) s_any = 1; }
+      // finished diagonals: every thread reads and clears its share (lanes of a warp hold 32 consecutive diagonals); only
+      // if some counter of the block reached the threshold are the seeds collected, in ascending order, by thread 0
+      for (int base = emit_lo; base < emit_hi; base += QG_SEED_STEP) {
+        uint32_t c[QG_SEED_PPT];
+        bool hot = false;
+#pragma unroll
+        for (int r = 0; r < QG_SEED_PPT; ++r) {
+          const int d = base + r * QG_SEED_THREADS + tid;
+          c[r] = 0;
+          if (d < emit_hi) {
+            const uint32_t idx = (uint32_t) (d + ylen) & mask;
+            c[r] = cnt[idx]; cnt[idx] = 0;
+            if (COUNTS) { counts_out[pd.count_off + (uint64_t) (d + span)] = c[r]; c[r] = 0; }     // memory-guided mode: raw counts only
+          }
+          hot = hot || ((int) c[r] >= threshold && c[r] > 0);
+        }
+        if (__syncthreads_or (hot ? 1 : 0)) {
+#pragma unroll
+          for (int r = 0; r < QG_SEED_PPT; ++r) {
+            const uint32_t m = __ballot_sync (QG_FULL_MASK, (int) c[r] >= threshold && c[r] > 0);
+            if (lane == 0) seedmask[r * (QG_SEED_THREADS / 32) + wid] = m;
           }
           __syncthreads ();
-          if (tid == 0 && s_any) {
-            s_any = 0;
+          if (tid == 0) {
             // seeds in ascending order -> union of [seed-half, seed+half] clipped to the matrix (diagenv.cpp:79-84)
             int open_lo = s_open_lo, open_hi = s_open_hi, have = s_have_open;
             uint32_t nr = s_nruns;
-            for (int g = 0; g < gcount; ++g) {
+            for (int g = 0; g < QG_SEED_STEP / 32; ++g) {
               uint32_t m = seedmask[g];
               while (m) {
-                const int b = __ffs ((int) m) - 1;
+                const int bb = __ffs ((int) m) - 1;
                 m &= m - 1;
-                const int seed = emit_lo + (g0 + g) * 32 + b;
+                const int seed = base + g * 32 + bb;
                 int lo = seed - half_band, hi = seed + half_band;
                 if (lo < min_diag) lo = min_diag;
                 if (hi > max_diag) hi = max_diag;
@@ -224,8 +223,6 @@ qg_seed_kernel (const qg_seed_item* __restrict__ items, const qg_pair_desc* __re
           }
           __syncthreads ();
         }
-      } else {
-        for (int d = emit_lo + tid; d < emit_hi; d += QG_SEED_THREADS) cnt[(uint32_t) (d + ylen) & mask] = 0;
       }
       __syncthreads ();
       emit_lo = emit_hi;

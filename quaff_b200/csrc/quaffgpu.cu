@@ -25,6 +25,18 @@ static int qg_upload (qg_ctx* ctx, qg_dbuf& b, const void* src, size_t bytes) {
   return QG_OK;
 }
 static int qg_download (qg_ctx* ctx, void* dst, const void* src, size_t bytes) {
+  if (bytes >= (256u << 10)) {
+    // large results go through a pinned staging buffer (DMA at link speed), then one host memcpy
+    if (ctx->h_pinned_cap < bytes) {
+      if (ctx->h_pinned) { cudaFreeHost (ctx->h_pinned); ctx->h_pinned = nullptr; ctx->h_pinned_cap = 0; }
+      QG_CUDA (ctx, cudaMallocHost (&ctx->h_pinned, bytes + bytes / 4));
+      ctx->h_pinned_cap = bytes + bytes / 4;
+    }
+    QG_CUDA (ctx, cudaMemcpyAsync (ctx->h_pinned, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    QG_CUDA (ctx, cudaStreamSynchronize (ctx->stream));
+    memcpy (dst, ctx->h_pinned, bytes);
+    return QG_OK;
+  }
   if (bytes) QG_CUDA (ctx, cudaMemcpyAsync (dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
   QG_CUDA (ctx, cudaStreamSynchronize (ctx->stream));
   return QG_OK;
@@ -129,6 +141,7 @@ extern "C" void qg_destroy (qg_ctx* ctx) {
   rel (ctx->omodel.d_match); rel (ctx->omodel.d_insert); rel (ctx->omodel.d_m2m); rel (ctx->omodel.d_m2i); rel (ctx->omodel.d_m2d);
   for (int s = 0; s < 2; ++s) { rel (ctx->omodel.d_pair[s]); rel (ctx->omodel.d_xonly[s]); rel (ctx->omodel.d_yonly[s]); rel (ctx->omodel.d_none[s]); }
   rel (ctx->d_lse);
+  if (ctx->h_pinned) cudaFreeHost (ctx->h_pinned);
   for (auto& b : ctx->scratch) rel (b);
   cudaEventDestroy (ctx->ev[0]); cudaEventDestroy (ctx->ev[1]);
   cudaEventDestroy (ctx->ev_fork);
@@ -286,6 +299,12 @@ static int qg_envelope_stage_cap (qg_ctx* ctx, const qg_dpconfig* cfg, uint64_t 
   std::vector<qg_pair_desc> pd (n_pairs);
   std::vector<qg_seed_item> items;
   bool any_sparse = false;
+  // diagonals per work item: large enough that the per-item index build is amortised, small enough to fill the GPU
+  uint64_t total_diags = 0;
+  for (size_t p = 0; p < n_pairs; ++p) if (xi[p] < X.n && yi[p] < Y.n) total_diags += (uint64_t) X.len (xi[p]) + Y.len (yi[p]);
+  int64_t chunk = (int64_t) (total_diags / (uint64_t) (16 * std::max (ctx->sm_count, 1)));
+  chunk = std::max<int64_t> (QG_SEED_CHUNK, std::min<int64_t> (chunk, 8 * QG_SEED_CHUNK));
+  chunk = (chunk / QG_SEED_STEP) * QG_SEED_STEP;
   const bool memory_mode = cfg->kmer_threshold < 0;
   std::vector<uint32_t> mem_pairs;
   uint64_t count_total = 0, bits_total = 0, hist_total = 0;
@@ -313,8 +332,8 @@ static int qg_envelope_stage_cap (qg_ctx* ctx, const qg_dpconfig* cfg, uint64_t 
       any_sparse = true;
       ymax = std::max (ymax, d.ylen);
       const int64_t dmin = -((int64_t) d.ylen - k), dmax = (int64_t) d.xlen - k;   // diagonals that can receive hits
-      for (int64_t b = dmin; b <= dmax; b += QG_SEED_CHUNK) {
-        qg_seed_item it; it.pair = (uint32_t) p; it.d_begin = (int32_t) b; it.d_end = (int32_t) std::min<int64_t> (b + QG_SEED_CHUNK, dmax + 1);
+      for (int64_t b = dmin; b <= dmax; b += chunk) {
+        qg_seed_item it; it.pair = (uint32_t) p; it.d_begin = (int32_t) b; it.d_end = (int32_t) std::min<int64_t> (b + chunk, dmax + 1);
         items.push_back (it);
       }
       runs_here = (uint64_t) (items.size () - d.item_begin) * run_cap + 1;
@@ -426,7 +445,7 @@ static int qg_envelope_stage_cap (qg_ctx* ctx, const qg_dpconfig* cfg, uint64_t 
 static int qg_envelope_stage (qg_ctx* ctx, const qg_dpconfig* cfg, uint64_t cell_size, int x_set,
                               size_t n_pairs, const uint32_t* xi, const uint32_t* yi, qg_env_result& out) {
   const uint32_t half = (uint32_t) cfg->band_size / 2;
-  const uint32_t cap_max = QG_SEED_CHUNK / (2 * half + 2) + 3;
+  const uint32_t cap_max = 8 * QG_SEED_CHUNK / (2 * half + 2) + 3;
   uint32_t cap = (uint32_t) qg_env_size ("QG_RUN_CAP", 64);
   while (true) {
     bool overflow = false;
@@ -612,7 +631,7 @@ static int qg_viterbi_impl (qg_ctx* ctx, const qg_dpconfig* cfg, size_t n_pairs,
   size_t freeb = 0, totb = 0;
   QG_CUDA (ctx, cudaMemGetInfo (&freeb, &totb));
   const uint64_t budget = (uint64_t) qg_env_size ("QG_TRACE_BUDGET_MB", std::min<size_t> (freeb / 2, (size_t) 32 << 30) >> 20) << 20;
-  std::vector<uint8_t> all_paths;
+  uint8_t* all_paths = nullptr;                              // grows by realloc: no zero fill, handed to the caller at the end
   std::vector<uint64_t> offs (n_pairs + 1, 0);
   uint64_t path_total = 0;
   const size_t step = group ? group : 1;
@@ -723,8 +742,10 @@ static int qg_viterbi_impl (qg_ctx* ctx, const qg_dpconfig* cfg, size_t n_pairs,
                    ctx->scratch[SC_PAIRDP].as<qg_pair_dp> (), (uint32_t) np, ctx->scratch[SC_PATHSCR].as<uint8_t> (),
                    ctx->scratch[SC_OUT3].as<uint32_t> (), ctx->scratch[SC_MISC1].as<uint64_t> (), ctx->scratch[SC_PATHOUT].as<uint8_t> ());
         QG_TRY (qg_check_launch (ctx, "qg_path_gather_kernel"));
-        all_paths.resize (path_total + goff[np]);
-        QG_TRY (qg_download (ctx, all_paths.data () + path_total, ctx->scratch[SC_PATHOUT].p, goff[np]));
+        uint8_t* grown = (uint8_t*) realloc (all_paths, path_total + goff[np] + 1);
+        if (!grown) { free (all_paths); QG_FAIL (ctx, QG_ERR_INVALID, "out of host memory"); }
+        all_paths = grown;
+        QG_TRY (qg_download (ctx, all_paths + path_total, ctx->scratch[SC_PATHOUT].p, goff[np]));
       }
       path_total += goff[np];
     }
@@ -733,10 +754,9 @@ static int qg_viterbi_impl (qg_ctx* ctx, const qg_dpconfig* cfg, size_t n_pairs,
   if (paths) {
     offs[n_pairs] = path_total;
     memcpy (path_offsets, offs.data (), sizeof (uint64_t) * (n_pairs + 1));
-    uint8_t* buf = (uint8_t*) malloc (path_total + 1);
-    if (!buf) QG_FAIL (ctx, QG_ERR_INVALID, "out of host memory");
-    if (path_total) memcpy (buf, all_paths.data (), path_total);
-    *path_out = buf;
+    if (!all_paths) all_paths = (uint8_t*) malloc (1);
+    if (!all_paths) QG_FAIL (ctx, QG_ERR_INVALID, "out of host memory");
+    *path_out = all_paths;
   }
   return QG_OK;
 }

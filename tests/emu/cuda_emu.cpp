@@ -15,6 +15,7 @@ void launch (dim3 grid, dim3 block, size_t smem, const std::function<void ()>& b
   for (unsigned w = 0; w < nwarps; ++w)
     pthread_barrier_init (&bs.warp_bar[w], NULL, std::min (32u, nthreads - w * 32));
   bs.xchg.assign (nwarps * 32, 0);
+  bs.or_flag = 0;
   bs.dyn_smem = (unsigned char*) malloc (smem + 16);
   for (unsigned by = 0; by < grid.y; ++by)
     for (unsigned bx = 0; bx < grid.x; ++bx) {

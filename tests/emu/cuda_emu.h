@@ -48,6 +48,7 @@ struct BlockState {
   std::vector<pthread_barrier_t> warp_bar;
   std::vector<uint64_t> xchg;        // one 64-bit slot per thread
   unsigned char* dyn_smem;
+  int or_flag;
 };
 extern thread_local uint3_e t_threadIdx, t_blockIdx;
 extern thread_local dim3 t_blockDim, t_gridDim;
@@ -82,6 +83,15 @@ void launch (dim3 grid, dim3 block, size_t smem, const std::function<void ()>& b
 
 static inline void __syncthreads () { pthread_barrier_wait (&qgemu::t_block->block_bar); }
 static inline void __syncwarp (unsigned = 0xffffffffu) { qgemu::warp_barrier (); }
+static inline int __syncthreads_or (int pred) {
+  if (pred) __atomic_store_n (&qgemu::t_block->or_flag, 1, __ATOMIC_RELAXED);
+  __syncthreads ();
+  const int r = __atomic_load_n (&qgemu::t_block->or_flag, __ATOMIC_RELAXED);
+  __syncthreads ();
+  if (threadIdx.x == 0) __atomic_store_n (&qgemu::t_block->or_flag, 0, __ATOMIC_RELAXED);
+  __syncthreads ();
+  return r;
+}
 template<class T> static inline T __shfl_sync (unsigned, T v, int src) { return qgemu::shfl_idx (v, src); }
 template<class T> static inline T __shfl_up_sync (unsigned, T v, unsigned d) {
   const int l = (int) qgemu::lane_id (); return qgemu::shfl_idx (v, l - (int) d >= 0 ? l - (int) d : l); }
