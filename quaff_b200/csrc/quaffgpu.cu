@@ -7,6 +7,7 @@
 #include "qg_backward.cuh"
 #include "qg_overlap.cuh"
 #include "qg_prob.cuh"
+#include "qg_tile.cuh"
 #include <map>
 #include <numeric>
 
@@ -615,17 +616,253 @@ static uint64_t qg_plan_cells (const qg_env_result& er, size_t p0, size_t p1) {
   return cu;
 }
 
+// ---- wide pairs: runs of more than 256 * QG_MAX_NW diagonals (qg_tile.cuh) -----------------------------------------
+static bool qg_pair_is_wide (const qg_env_result& er, size_t p) {
+  const uint32_t min_wide = (uint32_t) qg_env_size ("QG_WIDE_MIN_DIAGS", 256u * QG_MAX_NW);   // lowered by the tests only
+  for (uint32_t r = er.run_begin[p]; r < er.run_begin[p + 1]; ++r)
+    if ((uint32_t) (er.runs[r].y - er.runs[r].x + 1) > min_wide) return true;
+  return false;
+}
+
+// mode 0: Viterbi (+ traceback of the pairs flagged in want); mode 1: Forward log-likelihood.  idx: the wide pairs'
+// positions in the caller's pair list; outputs are written at those positions.
+static int qg_wide_run (qg_ctx* ctx, const qg_dpconfig* cfg, const qg_env_result& er, const std::vector<size_t>& idx,
+                        const uint32_t* xi, const uint32_t* yi, int mode, const uint8_t* want,
+                        double* score, uint32_t* x_start, uint32_t* x_end, std::vector<std::vector<uint8_t> >* paths) {
+  const qg_seqset& X = ctx->seqs[QG_REFS];
+  const qg_seqset& Y = ctx->seqs[QG_READS];
+  size_t freeb = 0, totb = 0;
+  QG_CUDA (ctx, cudaMemGetInfo (&freeb, &totb));
+  const uint64_t budget = (uint64_t) qg_env_size ("QG_TRACE_BUDGET_MB", std::min<size_t> (freeb / 2, (size_t) 48 << 30) >> 20) << 20;
+  size_t q0 = 0;
+  while (q0 < idx.size ()) {
+    // ---- plan a batch of pairs under the memory budget
+    std::vector<qg_wseg> segs; std::vector<qg_tile> tiles; std::vector<qg_wpair> wp; std::vector<long long> tables;
+    qg_dp_plan rpplan; std::map<uint32_t, uint64_t> rp_of_read;
+    uint64_t trace_words = 0, col_d = 0, row_d = 0, end_d = 0, bytes = 0, scratch_bytes = 0;
+    size_t q1 = q0;
+    while (q1 < idx.size ()) {
+      const size_t p = idx[q1];
+      const uint32_t xlen = X.len (xi[p]), ylen = Y.len (yi[p]);
+      const uint32_t nCB = (xlen + QG_TCW - 1) / QG_TCW, nRB = (ylen + QG_TRH - 1) / QG_TRH;
+      // count tiles of this pair first
+      uint64_t ntile = 0;
+      for (uint32_t r = er.run_begin[p]; r < er.run_begin[p + 1]; ++r)
+        for (uint32_t a = 0; a < nCB; ++a)
+          for (uint32_t b = 0; b < nRB; ++b) {
+            const int64_t iLo = (int64_t) a * QG_TCW + 1, iHi = std::min<int64_t> ((int64_t) (a + 1) * QG_TCW, xlen);
+            const int64_t jLo = (int64_t) b * QG_TRH + 1, jHi = std::min<int64_t> ((int64_t) (b + 1) * QG_TRH, ylen);
+            if (iHi - jLo >= er.runs[r].x && iLo - jHi <= er.runs[r].y) ++ntile;
+          }
+      const uint64_t nruns = er.run_begin[p + 1] - er.run_begin[p];
+      const uint64_t need = ntile * (mode == 0 ? QG_TILE_WORDS * 4ull : 0) + nruns * (((uint64_t) nCB + 1) * (ylen + 1) + ((uint64_t) nRB + 1) * (xlen + 1)) * 24
+                            + nruns * (uint64_t) nCB * nRB * 8 + (uint64_t) (xlen + 1) * 8 * nruns;
+      if (q1 > q0 && bytes + need > budget) break;
+      if (need > budget) QG_FAIL (ctx, QG_ERR_UNSUPPORTED, "pair %zu needs %llu MB of device memory for its %llu tiles (budget %llu MB)", p,
+                                  (unsigned long long) (need >> 20), (unsigned long long) ntile, (unsigned long long) (budget >> 20));
+      bytes += need;
+      qg_wpair w; memset (&w, 0, sizeof (w));
+      w.seg_begin = (uint32_t) segs.size (); w.tile_begin = (uint32_t) tiles.size (); w.xlen = xlen; w.ylen = ylen;
+      auto it = rp_of_read.find (yi[p]);
+      if (it == rp_of_read.end ()) {
+        qg_rp_job jb; jb.yseq = yi[p]; jb.ylen = ylen; jb.yoff = Y.off[yi[p]]; jb.rp_off = rpplan.rp_rows;
+        rpplan.rp_jobs.push_back (jb);
+        it = rp_of_read.insert (std::make_pair (yi[p], rpplan.rp_rows)).first;
+        rpplan.rp_rows += (uint64_t) ylen + 2;
+      }
+      int dmin = 0, dmax = 0; bool first = true;
+      for (uint32_t r = er.run_begin[p]; r < er.run_begin[p + 1]; ++r) {
+        qg_wseg ws; memset (&ws, 0, sizeof (ws));
+        ws.pair = (uint32_t) wp.size (); ws.xseq = xi[p]; ws.xlen = xlen; ws.ylen = ylen; ws.dlo = er.runs[r].x; ws.dhi = er.runs[r].y;
+        ws.nCB = nCB; ws.nRB = nRB; ws.rp_off = it->second;
+        ws.col_off = col_d; col_d += ((uint64_t) nCB + 1) * (ylen + 1) * 3;
+        ws.row_off = row_d; row_d += ((uint64_t) nRB + 1) * (xlen + 1) * 3;
+        ws.table_off = tables.size (); tables.resize (tables.size () + (size_t) nCB * nRB, -1);
+        ws.end_off = end_d; end_d += (uint64_t) xlen + 1;
+        for (uint32_t a = 0; a < nCB; ++a)
+          for (uint32_t b = 0; b < nRB; ++b) {
+            const int64_t iLo = (int64_t) a * QG_TCW + 1, iHi = std::min<int64_t> ((int64_t) (a + 1) * QG_TCW, xlen);
+            const int64_t jLo = (int64_t) b * QG_TRH + 1, jHi = std::min<int64_t> ((int64_t) (b + 1) * QG_TRH, ylen);
+            if (!(iHi - jLo >= ws.dlo && iLo - jHi <= ws.dhi)) continue;
+            qg_tile t; t.seg = (uint32_t) segs.size (); t.a = a; t.b = b; t.id = (uint32_t) tiles.size (); t.trace_off = trace_words;
+            tables[ws.table_off + (size_t) a * nRB + b] = (long long) trace_words;
+            if (mode == 0) trace_words += QG_TILE_WORDS;
+            tiles.push_back (t);
+          }
+        segs.push_back (ws);
+        if (first) { dmin = ws.dlo; dmax = ws.dhi; first = false; } else { dmin = std::min (dmin, ws.dlo); dmax = std::max (dmax, ws.dhi); }
+      }
+      w.seg_end = (uint32_t) segs.size (); w.tile_end = (uint32_t) tiles.size ();
+      const uint64_t xspan = std::min<uint64_t> (xlen, (uint64_t) ylen + (uint64_t) (dmax - dmin) + 1);
+      w.path_cap = (uint32_t) (ylen + xspan + 1);
+      w.want_path = (mode == 0 && want && want[p]) ? 1 : 0;
+      w.path_off = scratch_bytes;
+      if (w.want_path) scratch_bytes += w.path_cap;
+      wp.push_back (w);
+      ++q1;
+    }
+    const size_t np = wp.size ();
+    // tiles in wavefront order
+    std::vector<qg_tile> sorted (tiles);
+    std::stable_sort (sorted.begin (), sorted.end (), [] (const qg_tile& u, const qg_tile& v) { return u.a + u.b < v.a + v.b; });
+    {
+      qg_timer tm (ctx, &ctx->stats.ms_prep);
+      QG_TRY (qg_stage_rowparams (ctx, rpplan));
+      QG_TRY (qg_upload (ctx, ctx->scratch[SC_SEGS], segs.data (), sizeof (qg_wseg) * segs.size ()));
+      QG_TRY (qg_upload (ctx, ctx->scratch[SC_ITEMS], sorted.data (), sizeof (qg_tile) * sorted.size ()));
+      QG_TRY (qg_upload (ctx, ctx->scratch[SC_PAIRDP], wp.data (), sizeof (qg_wpair) * np));
+      QG_TRY (qg_upload (ctx, ctx->scratch[SC_MISC0], tables.data (), sizeof (long long) * tables.size ()));
+      QG_TRY (qg_reserve (ctx, ctx->scratch[SC_TRACE], sizeof (uint32_t) * (trace_words + 1)));
+      QG_TRY (qg_reserve (ctx, ctx->scratch[SC_STORE], sizeof (double) * (col_d + 1)));
+      QG_TRY (qg_reserve (ctx, ctx->scratch[SC_ROWACC], sizeof (double) * (row_d + 1)));
+      QG_TRY (qg_reserve (ctx, ctx->scratch[SC_ENDVALS], sizeof (double) * (std::max<uint64_t> (2 * tiles.size (), end_d) + 2)));
+      QG_TRY (qg_reserve (ctx, ctx->scratch[SC_OUT0], sizeof (double) * (np + 1)));
+      QG_TRY (qg_reserve (ctx, ctx->scratch[SC_OUT1], sizeof (uint32_t) * (np + 1)));
+      QG_TRY (qg_reserve (ctx, ctx->scratch[SC_OUT2], sizeof (uint32_t) * (np + 1)));
+      QG_TRY (qg_reserve (ctx, ctx->scratch[SC_OUT3], sizeof (uint32_t) * (np + 1)));
+      QG_TRY (qg_reserve (ctx, ctx->scratch[SC_PATHSCR], scratch_bytes + 16));
+    }
+    uint64_t cu = 0;
+    for (size_t q = q0; q < q1; ++q) cu += er.cu[idx[q]];
+    ctx->stats.cell_updates += cu;
+    ctx->stats.n_segments += segs.size ();
+    ctx->stats.trace_bytes += trace_words * 4;
+    qg_tile_args a;
+    memset (&a, 0, sizeof (a));
+    a.segs = ctx->scratch[SC_SEGS].as<qg_wseg> (); a.tiles = ctx->scratch[SC_ITEMS].as<qg_tile> ();
+    a.xpacked = X.d_packed.as<uint64_t> (); a.xpoff = X.d_poff.as<uint64_t> ();
+    a.rp = ctx->scratch[SC_RP].as<qg_rowp> (); a.lse = ctx->d_lse.as<double> ();
+    a.i2i = ctx->model.i2i; a.i2m = ctx->model.i2m; a.d2d = ctx->model.d2d; a.d2m = ctx->model.d2m; a.local = cfg->local;
+    a.trace = ctx->scratch[SC_TRACE].as<uint32_t> (); a.colbuf = ctx->scratch[SC_STORE].as<double> (); a.rowbuf = ctx->scratch[SC_ROWACC].as<double> ();
+    a.tile_best = ctx->scratch[SC_ENDVALS].as<double> (); a.endvals = ctx->scratch[SC_ENDVALS].as<double> ();
+    {
+      qg_timer tm (ctx, mode == 0 ? &ctx->stats.ms_viterbi : &ctx->stats.ms_forward);
+      size_t t0 = 0;
+      while (t0 < sorted.size ()) {                          // one launch per tile anti-diagonal
+        size_t t1 = t0; const uint32_t w = sorted[t0].a + sorted[t0].b;
+        while (t1 < sorted.size () && sorted[t1].a + sorted[t1].b == w) ++t1;
+        if (mode == 0) { QG_LAUNCH (qg_tile_kernel<0>, (unsigned) (t1 - t0), 32, 0, ctx->stream, a, (uint32_t) t0); }
+        else { QG_LAUNCH (qg_tile_kernel<1>, (unsigned) (t1 - t0), 32, 0, ctx->stream, a, (uint32_t) t0); }
+        QG_TRY (qg_check_launch (ctx, "qg_tile_kernel"));
+        t0 = t1;
+      }
+      if (mode == 0) {
+        QG_LAUNCH (qg_wide_score_kernel, (unsigned) ((np + 63) / 64), 64, 0, ctx->stream,
+                   ctx->scratch[SC_PAIRDP].as<qg_wpair> (), (uint32_t) np, ctx->scratch[SC_ENDVALS].as<double> (),
+                   ctx->scratch[SC_OUT0].as<double> (), ctx->scratch[SC_OUT2].as<uint32_t> ());
+        QG_TRY (qg_check_launch (ctx, "qg_wide_score_kernel"));
+      } else {
+        QG_LAUNCH (qg_wide_forward_finalize_kernel, (unsigned) ((np + 63) / 64), 64, 0, ctx->stream,
+                   ctx->scratch[SC_PAIRDP].as<qg_wpair> (), (uint32_t) np, ctx->scratch[SC_SEGS].as<qg_wseg> (),
+                   ctx->scratch[SC_ENDVALS].as<double> (), ctx->d_lse.as<double> (), ctx->scratch[SC_OUT0].as<double> ());
+        QG_TRY (qg_check_launch (ctx, "qg_wide_forward_finalize_kernel"));
+      }
+    }
+    std::vector<double> sc (np);
+    QG_TRY (qg_download (ctx, sc.data (), ctx->scratch[SC_OUT0].p, sizeof (double) * np));
+    for (size_t q = 0; q < np; ++q) score[idx[q0 + q]] = sc[q];
+    if (mode == 0 && x_start) {
+      std::vector<uint32_t> plen (np), xs (np), xe (np);
+      uint32_t flag = 0;
+      {
+        qg_timer tm (ctx, &ctx->stats.ms_traceback);
+        QG_CUDA (ctx, cudaMemsetAsync (ctx->scratch[SC_FLAGS].p, 0, 64, ctx->stream));
+        QG_LAUNCH (qg_wide_traceback_kernel, (unsigned) ((np + 31) / 32), 32, 0, ctx->stream,
+                   ctx->scratch[SC_PAIRDP].as<qg_wpair> (), (uint32_t) np, ctx->scratch[SC_SEGS].as<qg_wseg> (),
+                   ctx->scratch[SC_MISC0].as<long long> (), ctx->scratch[SC_TRACE].as<uint32_t> (), ctx->scratch[SC_OUT0].as<double> (),
+                   ctx->scratch[SC_OUT2].as<uint32_t> (), ctx->scratch[SC_OUT1].as<uint32_t> (), ctx->scratch[SC_PATHSCR].as<uint8_t> (),
+                   ctx->scratch[SC_OUT3].as<uint32_t> (), (uint32_t*) ctx->scratch[SC_FLAGS].p);
+        QG_TRY (qg_check_launch (ctx, "qg_wide_traceback_kernel"));
+      }
+      QG_TRY (qg_download (ctx, xs.data (), ctx->scratch[SC_OUT1].p, sizeof (uint32_t) * np));
+      QG_TRY (qg_download (ctx, xe.data (), ctx->scratch[SC_OUT2].p, sizeof (uint32_t) * np));
+      QG_TRY (qg_download (ctx, plen.data (), ctx->scratch[SC_OUT3].p, sizeof (uint32_t) * np));
+      QG_TRY (qg_download (ctx, &flag, ctx->scratch[SC_FLAGS].p, sizeof (uint32_t)));
+      if (flag) QG_FAIL (ctx, QG_ERR_CUDA, "internal: tiled traceback left the envelope (code %u)", flag);
+      std::vector<uint64_t> goff (np + 1, 0);
+      for (size_t q = 0; q < np; ++q) goff[q + 1] = goff[q] + plen[q];
+      std::vector<uint8_t> flat (goff[np] + 1);
+      if (goff[np]) {
+        QG_TRY (qg_upload (ctx, ctx->scratch[SC_MISC1], goff.data (), sizeof (uint64_t) * (np + 1)));
+        QG_TRY (qg_reserve (ctx, ctx->scratch[SC_PATHOUT], goff[np] + 16));
+        QG_LAUNCH (qg_wide_path_gather_kernel, (unsigned) np, 128, 0, ctx->stream,
+                   ctx->scratch[SC_PAIRDP].as<qg_wpair> (), (uint32_t) np, ctx->scratch[SC_PATHSCR].as<uint8_t> (),
+                   ctx->scratch[SC_OUT3].as<uint32_t> (), ctx->scratch[SC_MISC1].as<uint64_t> (), ctx->scratch[SC_PATHOUT].as<uint8_t> ());
+        QG_TRY (qg_check_launch (ctx, "qg_wide_path_gather_kernel"));
+        QG_TRY (qg_download (ctx, flat.data (), ctx->scratch[SC_PATHOUT].p, goff[np]));
+      }
+      for (size_t q = 0; q < np; ++q) {
+        const size_t p = idx[q0 + q];
+        const bool w = wp[q].want_path != 0;
+        x_start[p] = w ? xs[q] : 0; x_end[p] = w ? xe[q] : 0;
+        if (paths) (*paths)[p].assign (flat.begin () + goff[q], flat.begin () + goff[q + 1]);
+      }
+    }
+    q0 = q1;
+  }
+  return QG_OK;
+}
+
 // ---- Viterbi -------------------------------------------------------------------------------------------------------
 // group > 0: pairs come in consecutive groups of `group` (one read against every reference); the traceback then
 // runs only for the best-scoring pair of each group, earliest index on ties (qmodel.cpp:2773-2775).
 static int qg_viterbi_impl (qg_ctx* ctx, const qg_dpconfig* cfg, size_t n_pairs, const uint32_t* xi, const uint32_t* yi,
                             const uint8_t* want_path, size_t group, double* score, uint32_t* x_start, uint32_t* x_end,
-                            uint8_t** path_out, uint64_t* path_offsets) {
+                            uint8_t** path_out, uint64_t* path_offsets, const qg_env_result* er_in = nullptr) {
   QG_TRY (qg_check_ready (ctx, cfg));
   const bool paths = path_out && path_offsets && x_start && x_end;
   if (path_out) *path_out = nullptr;
-  qg_env_result er;
-  QG_TRY (qg_envelope_stage (ctx, cfg, 24, QG_REFS, n_pairs, xi, yi, er));
+  qg_env_result er_local;
+  if (!er_in) QG_TRY (qg_envelope_stage (ctx, cfg, 24, QG_REFS, n_pairs, xi, yi, er_local));
+  const qg_env_result& er = er_in ? *er_in : er_local;
+  if (!er_in) {
+    // pairs with runs too wide for one CTA take the tiled path (qg_tile.cuh); the rest continue below
+    std::vector<size_t> wide, narrow;
+    for (size_t p = 0; p < n_pairs; ++p) (qg_pair_is_wide (er, p) ? wide : narrow).push_back (p);
+    if (!wide.empty ()) {
+      // scores of every pair first, then the traceback selection (per group or per want_path), then both paths
+      std::vector<uint8_t> want (n_pairs, paths ? 1 : 0);
+      if (paths && !group && want_path) for (size_t p = 0; p < n_pairs; ++p) want[p] = want_path[p] ? 1 : 0;
+      std::vector<std::vector<uint8_t> > per_pair (n_pairs);
+      std::vector<uint32_t> xs (n_pairs, 0), xe (n_pairs, 0);
+      QG_TRY (qg_wide_run (ctx, cfg, er, wide, xi, yi, 0, want.data (), score, paths ? xs.data () : nullptr, paths ? xe.data () : nullptr, paths ? &per_pair : nullptr));
+      if (!narrow.empty ()) {
+        qg_env_result sub; std::vector<uint32_t> sxi, syi; std::vector<uint8_t> swant;
+        sub.run_begin.push_back (0);
+        for (size_t p : narrow) {
+          for (uint32_t r = er.run_begin[p]; r < er.run_begin[p + 1]; ++r) sub.runs.push_back (er.runs[r]);
+          sub.run_begin.push_back ((uint32_t) sub.runs.size ()); sub.cu.push_back (er.cu[p]); sub.ndiag.push_back (er.ndiag[p]);
+          sxi.push_back (xi[p]); syi.push_back (yi[p]); swant.push_back (want[p]);
+        }
+        std::vector<double> ssc (narrow.size ()); std::vector<uint32_t> sxs (narrow.size ()), sxe (narrow.size ()); std::vector<uint64_t> soff (narrow.size () + 1);
+        uint8_t* sp = nullptr;
+        QG_TRY (qg_viterbi_impl (ctx, cfg, narrow.size (), sxi.data (), syi.data (), swant.data (), 0, ssc.data (), paths ? sxs.data () : nullptr,
+                                 paths ? sxe.data () : nullptr, paths ? &sp : nullptr, paths ? soff.data () : nullptr, &sub));
+        for (size_t q = 0; q < narrow.size (); ++q) {
+          const size_t p = narrow[q];
+          score[p] = ssc[q];
+          if (paths) { xs[p] = sxs[q]; xe[p] = sxe[q]; per_pair[p].assign (sp + soff[q], sp + soff[q + 1]); }
+        }
+        free (sp);
+      }
+      if (paths) {
+        // group mode: keep the best pair of each group only
+        if (group) for (size_t g0 = 0; g0 < n_pairs; g0 += group) {
+          size_t best = g0; bool any = false;
+          for (size_t q = g0; q < std::min (n_pairs, g0 + group); ++q) if (score[q] > -INFINITY && (!any || score[q] > score[best])) { best = q; any = true; }
+          for (size_t q = g0; q < std::min (n_pairs, g0 + group); ++q) if (!any || q != best) { per_pair[q].clear (); xs[q] = 0; xe[q] = 0; }
+        }
+        uint64_t total = 0;
+        for (size_t p = 0; p < n_pairs; ++p) { path_offsets[p] = total; total += per_pair[p].size (); x_start[p] = xs[p]; x_end[p] = xe[p]; }
+        path_offsets[n_pairs] = total;
+        uint8_t* buf = (uint8_t*) malloc (total + 1);
+        if (!buf) QG_FAIL (ctx, QG_ERR_INVALID, "out of host memory");
+        for (size_t p = 0; p < n_pairs; ++p) if (!per_pair[p].empty ()) memcpy (buf + path_offsets[p], per_pair[p].data (), per_pair[p].size ());
+        *path_out = buf;
+      }
+      return QG_OK;
+    }
+  }
 
   // sub-batches bounded by pointer memory
   size_t freeb = 0, totb = 0;
@@ -872,6 +1109,20 @@ extern "C" int qg_forward (qg_ctx* ctx, const qg_dpconfig* cfg, size_t n_pairs, 
   QG_TRY (qg_check_ready (ctx, cfg));
   qg_env_result er;
   QG_TRY (qg_envelope_stage (ctx, cfg, 48, QG_REFS, n_pairs, xi, yi, er));
+  {
+    std::vector<size_t> wide, narrow;
+    for (size_t p = 0; p < n_pairs; ++p) (qg_pair_is_wide (er, p) ? wide : narrow).push_back (p);
+    if (!wide.empty ()) {
+      QG_TRY (qg_wide_run (ctx, cfg, er, wide, xi, yi, 1, nullptr, loglike, nullptr, nullptr, nullptr));
+      if (!narrow.empty ()) {                               // the rest through the ordinary path (their envelopes are recomputed: rare, mixed calls only)
+        std::vector<uint32_t> sxi, syi; std::vector<double> sll (narrow.size ());
+        for (size_t p : narrow) { sxi.push_back (xi[p]); syi.push_back (yi[p]); }
+        QG_TRY (qg_forward (ctx, cfg, narrow.size (), sxi.data (), syi.data (), sll.data ()));
+        for (size_t q = 0; q < narrow.size (); ++q) loglike[narrow[q]] = sll[q];
+      }
+      return QG_OK;
+    }
+  }
   qg_dp_plan plan;
   QG_TRY (qg_build_plan (ctx, er, 0, n_pairs, xi, yi, QG_REFS, 1, plan));
   // Forward folds end values per pair in pair order: keep segs in pair order, launch classes through an index

@@ -103,3 +103,29 @@ def test_emu_probability_space_forward_backward(emu, oracle, workload):
     nullp = QuaffNullParams.load(os.path.join(os.path.dirname(__file__), "golden", "testquaffnullparams.json"))
     pc.check_estep(emu, oracle, x, reads, s_or, nullp, cfg, use_null=True, n_iter=1, exact=False)
     emu.set_fb_exact(True)
+
+
+def test_emu_wide_runs_tiled(emu_lib, oracle, monkeypatch):
+    """runs wider than one CTA's 8192 diagonals take the i-space tile wavefront (qg_tile.cuh): -kmatchoff on an
+    8.2 kb reference gives one run of > 8192 diagonals; Viterbi (score, interval, path) and Forward stay bit-exact.
+    The second half lowers the width threshold so that sparse multi-run envelopes go through the tiles as well."""
+    qp = pc.default_params()
+    s_or = oracle.scores(qp)
+    g = api.QuaffGPU(lib_path=emu_lib)
+    try:
+        x, reads = pc.make_workload(ref_len=8200, n_reads=1, read_len=120, seed=11)
+        g.set_refs(x); g.set_reads(reads); g.set_params(qp)
+        xi, yi = pc.all_pairs(len(x), len(reads))
+        for local in (True, False):
+            cfg = api.dp_config(sparse=False, local=local)
+            pc.check_viterbi(g, oracle, x, reads, s_or, cfg, xi, yi)
+            pc.check_forward(g, oracle, x, reads, s_or, cfg, xi, yi)
+        monkeypatch.setenv("QG_WIDE_MIN_DIAGS", "40")
+        x, reads = pc.make_workload(ref_len=1500, n_reads=2, read_len=300, seed=5)
+        g.set_refs(x); g.set_reads(reads); g.set_params(qp)
+        xi, yi = pc.all_pairs(len(x), len(reads))
+        for cfg in (api.dp_config(kmer_threshold=3, band_size=20), api.dp_config(kmer_threshold=6, local=False)):
+            pc.check_viterbi(g, oracle, x, reads, s_or, cfg, xi, yi)
+            pc.check_forward(g, oracle, x, reads, s_or, cfg, xi, yi)
+    finally:
+        g.close()

@@ -155,3 +155,43 @@ def test_probability_space_order2_and_global(gpu, oracle):
         pc.check_forward(gpu, oracle, x, reads, s_or, cfg, xi, yi, exact=False)
         pc.check_backward(gpu, oracle, x, reads, s_or, cfg, xi, yi, exact=False)
     gpu.set_fb_exact(True)
+
+
+def test_wide_runs_tiled(gpu, oracle):
+    """-kmatchoff on 20 kb references: one run of > 8192 diagonals per pair goes through the i-space tile
+    wavefront (qg_tile.cuh); Viterbi score / interval / path and Forward stay bit-exact"""
+    x, reads = pc.make_workload(ref_len=20000, n_reads=3, read_len=2000, seed=23, n_refs=2)
+    qp = pc.default_params()
+    gpu.set_refs(x); gpu.set_reads(reads); gpu.set_params(qp)
+    s_or = oracle.scores(qp)
+    xi, yi = pc.all_pairs(len(x), len(reads))
+    for local in (True, False):
+        cfg = api.dp_config(sparse=False, local=local)
+        pc.check_viterbi(gpu, oracle, x, reads, s_or, cfg, xi, yi)
+        pc.check_forward(gpu, oracle, x, reads, s_or, cfg, xi, yi)
+
+
+def test_wide_and_narrow_pairs_mixed(gpu, oracle, workload, monkeypatch):
+    """lowering the width threshold sends some pairs of a call through the tiles and the rest through the
+    warp-per-run kernels: align_reads (best reference per read) must not change"""
+    x, reads, s_or = workload
+    cfg = api.dp_config(kmer_threshold=14)
+    null_ll = np.zeros(len(reads))
+    a0 = gpu.align_reads(cfg, null_ll)
+    xi, yi = pc.all_pairs(len(x), len(reads))
+    diags, _ = gpu.envelopes(cfg, xi, yi)
+
+    def widest_run(d):
+        cuts = np.flatnonzero(np.diff(d) != 1)
+        return int(np.diff(np.concatenate(([-1], cuts, [len(d) - 1]))).max()) if len(d) else 0
+    widths = sorted(widest_run(d) for d in diags)
+    assert widths[0] < widths[-1]
+    monkeypatch.setenv("QG_WIDE_MIN_DIAGS", str((widths[0] + widths[-1]) // 2))   # pairs on both sides of the threshold
+    a1 = gpu.align_reads(cfg, null_ll)
+    f1 = pc.check_forward(gpu, oracle, x, reads, s_or, cfg, xi, yi)
+    monkeypatch.delenv("QG_WIDE_MIN_DIAGS")
+    assert np.array_equal(a0["best_ref"], a1["best_ref"]) and np.array_equal(a0["score"], a1["score"])
+    assert np.array_equal(a0["x_start"], a1["x_start"]) and np.array_equal(a0["x_end"], a1["x_end"])
+    for p0, p1 in zip(a0["paths"], a1["paths"]):
+        assert np.array_equal(p0, p1)
+    assert np.isfinite(f1).any()
