@@ -32,6 +32,7 @@ struct qg_pair_desc {
   uint32_t run_out;                  // offset of this pair's merged runs in pair_runs
   uint32_t run_cap;                  // memory-guided mode: capacity of that region
   uint32_t pad_;
+  uint64_t idx_off;                  // general seeding path: offset of the read's sorted (k-mer, position) index
   uint64_t count_off;                // memory-guided mode: offset of this pair's per-diagonal counts
   uint64_t bits_off;                 // memory-guided mode: word offset of this pair's three bitmaps
   uint64_t hist_off;                 // memory-guided mode: offset of this pair's count histogram
@@ -299,7 +300,7 @@ __global__ void qg_envelope_finalize_kernel (const qg_pair_desc* __restrict__ pa
 // so clarity over speed: two passes over the pair's per-diagonal counts per non-empty tier.
 __global__ void __launch_bounds__ (256)
 qg_memtier_kernel (const qg_pair_desc* __restrict__ pairs, const uint32_t* __restrict__ pair_ids, const uint32_t* __restrict__ counts,
-                   uint32_t* __restrict__ hist_all, uint32_t* __restrict__ bits_all, int k, int half_band,
+                   uint32_t* __restrict__ hist_all, uint32_t* __restrict__ bits_all, int k, int half_band, int fixed_threshold,
                    unsigned long long cell_size, unsigned long long max_size,
                    int2* __restrict__ pair_runs, uint2* __restrict__ pair_info, uint32_t* __restrict__ overflow_flag) {
   __shared__ uint32_t s_cmax, s_new;
@@ -329,6 +330,16 @@ qg_memtier_kernel (const qg_pair_desc* __restrict__ pairs, const uint32_t* __res
   if (tid == 0) { const int b = 0 + ylen + 1; accepted[b >> 5] |= 1u << (b & 31); env[b >> 5] |= 1u << (b & 31); }   // diags = storageDiags = {0}
   __syncthreads ();
   const uint32_t cmax = s_cmax;
+  if (fixed_threshold >= 0) {
+    // plain -kmatchn threshold on the general path's global counts (diagenv.cpp:62-96 with kmerThreshold >= 0)
+    for (int t = tid; t < ndiag; t += blockDim.x)
+      if (cnt[t] >= (uint32_t) fixed_threshold) {
+        const int seed = t - span;
+        const int lo = seed - half_band > min_diag ? seed - half_band : min_diag;
+        const int hi = seed + half_band < max_diag ? seed + half_band : max_diag;
+        for (int d = lo; d <= hi; ++d) { const int b = d + ylen + 1; atomicOr (&env[b >> 5], 1u << (b & 31)); }
+      }
+  } else
   for (uint32_t c = cmax; c >= 1; --c) {
     if (hist[c] == 0) continue;
     for (int t = tid; t < ndiag; t += blockDim.x)
@@ -375,6 +386,58 @@ qg_memtier_kernel (const qg_pair_desc* __restrict__ pairs, const uint32_t* __res
     if (open) { if (n < pd.run_cap) out[n] = make_int2 (run_lo, nwords * 32 - 1 - ylen - 1); else *overflow_flag = 2; ++n; }
     pair_info[p] = make_uint2 (n < pd.run_cap ? n : pd.run_cap, 0);
   }
+}
+
+
+// ---- general seeding path: any k <= 32, any read length ----------------------------------------------------------
+// Used when the shared-memory kernel above does not apply (k outside 5..7, or a read whose bucket index and counter
+// ring do not fit one CTA's shared memory).  The read's k-mer starts are radix-sorted by k-mer (the GPU form of
+// KmerIndex's map, fastseq.cpp:240-256); every reference position binary-searches its k-mer and increments the
+// pair's per-diagonal counters in HBM (diagenv.cpp:33-41); qg_memtier_kernel turns the counters into runs.
+__global__ void qg_codes64_kernel (const uint8_t* __restrict__ tok, const uint64_t* __restrict__ off, uint32_t nseq,
+                                   uint64_t total, int k, unsigned long long* __restrict__ codes) {
+  const uint64_t g = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (g < total) {
+    uint32_t lo = 0, hi = nseq;
+    while (hi - lo > 1) { const uint32_t mid = (lo + hi) / 2; if (off[mid] <= g) lo = mid; else hi = mid; }
+    const uint64_t end = off[lo + 1];
+    unsigned long long code = 0;
+    if (g + k <= end) for (int t = 0; t < k; ++t) code = code * 4 + (tok[g + t] & 3);
+    codes[g] = code;                                       // positions without a k-mer are never read (bounds come from the lengths)
+  }
+}
+
+struct qg_index_job { uint64_t yoff; uint64_t idx_off; uint32_t n; uint32_t pad_; };   // one per distinct read: n = yLen - k + 1 k-mer starts
+
+__global__ void qg_index_fill_kernel (const qg_index_job* __restrict__ jobs, const unsigned long long* __restrict__ ycodes,
+                                      unsigned long long* __restrict__ keys, uint32_t* __restrict__ vals) {
+  const qg_index_job jb = jobs[blockIdx.y];
+  for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < jb.n; j += gridDim.x * blockDim.x) {
+    keys[jb.idx_off + j] = ycodes[jb.yoff + j];
+    vals[jb.idx_off + j] = j;
+  }
+}
+
+__global__ void __launch_bounds__ (256)
+qg_seed_general_kernel (const qg_seed_item* __restrict__ items, const qg_pair_desc* __restrict__ pairs,
+                        const unsigned long long* __restrict__ xcodes, const unsigned long long* __restrict__ keys,
+                        const uint32_t* __restrict__ vals, int k, uint32_t* __restrict__ counts, unsigned long long* __restrict__ hit_counter) {
+  const qg_seed_item it = items[blockIdx.x];               // d_begin / d_end: reference positions [i_begin, i_end)
+  const qg_pair_desc pd = pairs[it.pair];
+  const uint32_t n = pd.ylen - (uint32_t) k + 1;
+  const unsigned long long* ky = keys + pd.idx_off;
+  const uint32_t* vy = vals + pd.idx_off;
+  uint32_t* cnt = counts + pd.count_off;
+  const int span = (int) pd.ylen - k;
+  unsigned long long hits = 0;
+  for (int i = it.d_begin + (int) threadIdx.x; i < it.d_end; i += (int) blockDim.x) {
+    const unsigned long long code = xcodes[pd.xoff + (uint64_t) i];
+    uint32_t lo = 0, hi = n;                               // first entry with key >= code
+    while (lo < hi) { const uint32_t mid = (lo + hi) / 2; if (ky[mid] < code) lo = mid + 1; else hi = mid; }
+    for (uint32_t e = lo; e < n && ky[e] == code; ++e) { atomicAdd (&cnt[i - (int) vy[e] + span], 1u); ++hits; }
+  }
+  for (int o = 16; o > 0; o >>= 1) hits += __shfl_down_sync (0xffffffffu, hits, o);
+  if ((threadIdx.x & 31) == 0 && hits) atomicAdd (hit_counter, hits);
 }
 
 #endif

@@ -20,13 +20,14 @@ struct qg_wseg {                       // one run of a "wide" pair
   int32_t dlo, dhi;
   uint32_t nCB, nRB;
   uint64_t rp_off;
-  uint64_t col_off;                    // doubles: [(nCB+1)][(ylen+1)][3]  last column of every column block
-  uint64_t row_off;                    // doubles: [(nRB+1)][(xlen+1)][3]  last row of every row block
-  uint64_t table_off;                  // int64 [nCB][nRB]: word offset of the tile's pointer block, -1 if the tile is empty
+  uint64_t table_off;                  // int64 [nCB][nRB]: id of the tile, -1 if the run does not touch it
   uint64_t end_off;                    // Forward: doubles [xlen+1], M(i,yLen)+m2e per column
 };
 
-struct qg_tile { uint32_t seg, a, b, id; uint64_t trace_off; };     // id: index in pair order (tile_best slot)
+// id: index in pair order; it addresses the tile's pointer block (id * QG_TILE_WORDS), its last-column slice
+// (id * QG_TRH * 3 doubles), its last-row slice (id * QG_TCW * 3 doubles) and its tile_best slot.
+// left / up / diag: ids of the tiles (a-1,b), (a,b-1), (a-1,b-1) of the same run, -1 where the run does not touch them
+struct qg_tile { uint32_t seg, a, b, id; int32_t left, up, diag, pad_; };
 
 struct qg_tile_args {
   const qg_wseg* segs;
@@ -38,8 +39,8 @@ struct qg_tile_args {
   double i2i, i2m, d2d, d2m;
   int local;
   uint32_t* trace;
-  double* colbuf;
-  double* rowbuf;
+  double* colbuf;                      // [tile][QG_TRH][3]  last column of every tile
+  double* rowbuf;                      // [tile][QG_TCW][3]  last row of every tile
   double* tile_best;                   // Viterbi: {score, i} per tile of the last row block
   double* endvals;                     // Forward
 };
@@ -61,10 +62,13 @@ qg_tile_kernel (const qg_tile_args a, uint32_t tile_begin) {
   const int i0 = (int) tl.a * QG_TCW + 1 + lane * QG_TRC;        // my first column (1-based)
   const int j0 = (int) tl.b * QG_TRH + 1;                        // first row of the tile
   const int jend = (j0 + QG_TRH - 1 < ylen) ? j0 + QG_TRH - 1 : ylen;   // last row of the tile
-  double* colIn = a.colbuf + ws.col_off + (uint64_t) tl.a * (ylen + 1) * 3;           // column i0 - 1 of lane 0 = a * TCW
-  double* colOut = a.colbuf + ws.col_off + (uint64_t) (tl.a + 1) * (ylen + 1) * 3;
-  const double* rowIn = a.rowbuf + ws.row_off + (uint64_t) tl.b * (xlen + 1) * 3;     // row j0 - 1
-  double* rowOut = a.rowbuf + ws.row_off + (uint64_t) (tl.b + 1) * (xlen + 1) * 3;
+  const int ti0 = (int) tl.a * QG_TCW + 1;                       // first column of the tile
+  // edge slices, addressed relative to the tile: column slices by j - j0, row slices by i - ti0
+  const double* colIn = a.colbuf + ((int64_t) (tl.left < 0 ? 0 : tl.left) * (QG_TRH * 3) - (int64_t) j0 * 3);    // column ti0 - 1
+  double* colOut = a.colbuf + ((int64_t) tl.id * (QG_TRH * 3) - (int64_t) j0 * 3);
+  const double* rowIn = a.rowbuf + ((int64_t) (tl.up < 0 ? 0 : tl.up) * (QG_TCW * 3) - (int64_t) ti0 * 3);       // row j0 - 1
+  double* rowOut = a.rowbuf + ((int64_t) tl.id * (QG_TCW * 3) - (int64_t) ti0 * 3);
+  const double* diagIn = a.rowbuf + (uint64_t) (tl.diag < 0 ? 0 : tl.diag) * (QG_TCW * 3) + (uint64_t) (QG_TCW - 1) * 3;   // (ti0 - 1, j0 - 1)
 
   // row j0-1 of my columns, and of the column to my left
   double M[QG_TRC], I[QG_TRC], D[QG_TRC];
@@ -72,19 +76,21 @@ qg_tile_kernel (const qg_tile_args a, uint32_t tile_begin) {
 #pragma unroll
   for (int c = 0; c < QG_TRC; ++c) {
     const int i = i0 + c, jt = j0 - 1;
-    const bool have = tl.b > 0 && i <= xlen && (i - jt) >= dlo && (i - jt) <= dhi;
-    M[c] = have ? rowIn[(uint64_t) i * 3] : QG_NEG_INF;
-    I[c] = have ? rowIn[(uint64_t) i * 3 + 1] : QG_NEG_INF;
-    D[c] = have ? rowIn[(uint64_t) i * 3 + 2] : QG_NEG_INF;
+    const bool have = tl.up >= 0 && i <= xlen && (i - jt) >= dlo && (i - jt) <= dhi;
+    M[c] = have ? rowIn[(int64_t) i * 3] : QG_NEG_INF;
+    I[c] = have ? rowIn[(int64_t) i * 3 + 1] : QG_NEG_INF;
+    D[c] = have ? rowIn[(int64_t) i * 3 + 2] : QG_NEG_INF;
     tok[c] = qg_tok (xw, nxw, i - 1);
   }
   double tlM, tlI, tlD;                                          // (i0-1, j0-1)
   {
     const int i = i0 - 1, jt = j0 - 1;
-    const bool have = tl.b > 0 && i >= 1 && (i - jt) >= dlo && (i - jt) <= dhi;
-    tlM = have ? rowIn[(uint64_t) i * 3] : QG_NEG_INF;
-    tlI = have ? rowIn[(uint64_t) i * 3 + 1] : QG_NEG_INF;
-    tlD = have ? rowIn[(uint64_t) i * 3 + 2] : QG_NEG_INF;
+    // lane 0's upper-left cell lies in the tile (a-1, b-1); the other lanes' in the tile above
+    const double* src = (lane == 0) ? diagIn : rowIn + (int64_t) i * 3;
+    const bool have = (lane == 0 ? tl.diag >= 0 : tl.up >= 0) && i >= 1 && jt >= 1 && (i - jt) >= dlo && (i - jt) <= dhi;
+    tlM = have ? src[0] : QG_NEG_INF;
+    tlI = have ? src[1] : QG_NEG_INF;
+    tlD = have ? src[2] : QG_NEG_INF;
   }
   double l1M = QG_NEG_INF, l1I = QG_NEG_INF, l1D = QG_NEG_INF;   // left column at my current row (from the left lane / colIn)
   double pvM = QG_NEG_INF, pvI = QG_NEG_INF, pvD = QG_NEG_INF;   // ... and at my previous row
@@ -100,10 +106,10 @@ qg_tile_kernel (const qg_tile_args a, uint32_t tile_begin) {
     // lane at the end of the previous step (that lane is one row ahead); at row j-1: what was "row j" one step ago
     if (lane == 0) {
       const int i = i0 - 1;
-      const bool have = active && tl.a > 0 && (i - j) >= dlo && (i - j) <= dhi;
-      l1M = have ? colIn[(uint64_t) j * 3] : QG_NEG_INF;
-      l1I = have ? colIn[(uint64_t) j * 3 + 1] : QG_NEG_INF;
-      l1D = have ? colIn[(uint64_t) j * 3 + 2] : QG_NEG_INF;
+      const bool have = active && tl.left >= 0 && (i - j) >= dlo && (i - j) <= dhi;
+      l1M = have ? colIn[(int64_t) j * 3] : QG_NEG_INF;
+      l1I = have ? colIn[(int64_t) j * 3 + 1] : QG_NEG_INF;
+      l1D = have ? colIn[(int64_t) j * 3 + 2] : QG_NEG_INF;
     }
     double l0M = pvM, l0I = pvI, l0D = pvD;
     if (u == lane) { l0M = tlM; l0I = tlI; l0D = tlD; }          // first row of the tile: (i0-1, j0-1) comes from the row above
@@ -150,20 +156,20 @@ qg_tile_kernel (const qg_tile_args a, uint32_t tile_begin) {
         else if (i <= xlen) a.endvals[ws.end_off + i] = isEnd ? nM + m2e : QG_NEG_INF;
       }
     }
-    if (MODE == 0) a.trace[tl.trace_off + (uint64_t) u * 32 + lane] = tword;
+    if (MODE == 0) a.trace[(uint64_t) tl.id * QG_TILE_WORDS + (uint64_t) u * 32 + lane] = tword;
     // my last column at row j goes to the right lane (its row j at the next step) / to the column buffer of the next tile
     {
       const double sM = active ? M[QG_TRC - 1] : QG_NEG_INF, sI = active ? I[QG_TRC - 1] : QG_NEG_INF, sD = active ? D[QG_TRC - 1] : QG_NEG_INF;
       const double rM = __shfl_up_sync (QG_FULL_MASK, sM, 1), rI = __shfl_up_sync (QG_FULL_MASK, sI, 1), rD = __shfl_up_sync (QG_FULL_MASK, sD, 1);
       pvM = l1M; pvI = l1I; pvD = l1D;
       if (lane > 0) { l1M = rM; l1I = rI; l1D = rD; }
-      if (lane == 31 && active) { colOut[(uint64_t) j * 3] = sM; colOut[(uint64_t) j * 3 + 1] = sI; colOut[(uint64_t) j * 3 + 2] = sD; }
+      if (lane == 31 && active) { colOut[(int64_t) j * 3] = sM; colOut[(int64_t) j * 3 + 1] = sI; colOut[(int64_t) j * 3 + 2] = sD; }
     }
     if (active && j == jend) {
 #pragma unroll
       for (int c = 0; c < QG_TRC; ++c) {
         const int i = i0 + c;
-        if (i <= xlen) { rowOut[(uint64_t) i * 3] = M[c]; rowOut[(uint64_t) i * 3 + 1] = I[c]; rowOut[(uint64_t) i * 3 + 2] = D[c]; }
+        if (i <= xlen) { rowOut[(int64_t) i * 3] = M[c]; rowOut[(int64_t) i * 3 + 1] = I[c]; rowOut[(int64_t) i * 3 + 2] = D[c]; }
       }
     }
   }
@@ -235,9 +241,10 @@ __global__ void qg_wide_traceback_kernel (const qg_wpair* __restrict__ pairs, ui
     const int ta = (i - 1) / QG_TCW, tb = (j - 1) / QG_TRH;
     const long long toff = tables[ws.table_off + (uint64_t) ta * ws.nRB + tb];
     if (toff < 0) { *err_flag = 4; break; }
+    const uint64_t tbase = (uint64_t) toff * QG_TILE_WORDS;
     const int ci = (i - 1) - ta * QG_TCW, ln = ci / QG_TRC, c = ci - ln * QG_TRC;
     const int u = (j - 1 - tb * QG_TRH) + ln;
-    const uint32_t nib = (trace[(uint64_t) toff + (uint64_t) u * 32 + ln] >> (4 * c)) & 15u;
+    const uint32_t nib = (trace[tbase + (uint64_t) u * 32 + ln] >> (4 * c)) & 15u;
     if (n >= pd.path_cap) { *err_flag = 2; break; }
     if (state == 1) { buf[pd.path_cap - 1 - n] = QG_OP_MATCH; ++n; --i; --j; const uint32_t src = nib & 3u; state = (src == 0) ? 1 : (src == 1) ? 2 : (src == 2) ? 3 : 0; }
     else if (state == 2) { buf[pd.path_cap - 1 - n] = QG_OP_INSERT; ++n; --j; state = (nib & 4u) ? 2 : 1; }

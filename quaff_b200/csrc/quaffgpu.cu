@@ -8,6 +8,9 @@
 #include "qg_overlap.cuh"
 #include "qg_prob.cuh"
 #include "qg_tile.cuh"
+#ifndef QG_EMU
+#include <cub/device/device_segmented_radix_sort.cuh>
+#endif
 #include <map>
 #include <numeric>
 
@@ -16,7 +19,8 @@ static qg_error g_create_error;
 enum {
   SC_PAIRDESC = 0, SC_ITEMS, SC_ITEMRUNS, SC_ITEMNRUNS, SC_PAIRRUNS, SC_PAIRINFO, SC_PAIRCU, SC_FLAGS,
   SC_SEGS, SC_RPJOBS, SC_RP, SC_TRACE, SC_ENDVALS, SC_PAIRDP, SC_OUT0, SC_OUT1, SC_OUT2, SC_OUT3, SC_PATHSCR, SC_PATHOUT,
-  SC_STORE, SC_ROWACC, SC_MISC0, SC_MISC1, SC_RQ, SC_RS, SC_ENDEX, SC_STOREEX, SC_ZM, SC_ZE
+  SC_STORE, SC_ROWACC, SC_MISC0, SC_MISC1, SC_RQ, SC_RS, SC_ENDEX, SC_STOREEX, SC_ZM, SC_ZE,
+  SC_XC64, SC_YC64, SC_KEYS0, SC_KEYS1, SC_VALS0, SC_VALS1, SC_IDXJOBS, SC_SEGOFF, SC_SORTTMP
 };
 
 // ---- small helpers -----------------------------------------------------------------------------------
@@ -291,6 +295,80 @@ struct qg_env_result {
   std::vector<uint32_t> ndiag;       // [n_pairs]
 };
 
+// which seeding kernel serves this pair list: the shared-memory histogram kernel (k in 5..7, index + ring fit one CTA)
+// or the general path (sorted read index + per-diagonal counters in HBM)
+static size_t qg_seed_smem_bytes (int k, uint32_t ymax, uint32_t* ring_out) {
+  const uint32_t nk = 1u << (2 * k);
+  uint32_t need = std::max<uint32_t> (nk, QG_SEED_STEP + ymax + 1), ring = 1;
+  while (ring < need) ring <<= 1;
+  if (ring_out) *ring_out = ring;
+  return (size_t) ring * 4 + (size_t) nk * 4 + (size_t) ((ymax + 2) & ~1u) * 2 + (QG_SEED_STEP / 32 + 2) * 4;
+}
+static bool qg_pair_is_sparse (const qg_dpconfig* cfg, uint32_t xlen, uint32_t ylen) {
+  if (!cfg->sparse) return false;
+  if (cfg->kmer_threshold >= 0) {                              // diagenv.cpp:23-29
+    const uint32_t min_len = 2u * (uint32_t) (cfg->kmer_len + cfg->kmer_threshold);
+    if (xlen < min_len || ylen < min_len) return false;
+  }
+  return true;
+}
+static bool qg_seed_is_general (qg_ctx* ctx, const qg_dpconfig* cfg, int x_set, size_t n_pairs, const uint32_t* xi, const uint32_t* yi) {
+  const qg_seqset& X = ctx->seqs[x_set];
+  const qg_seqset& Y = ctx->seqs[QG_READS];
+  uint32_t ymax = 0; bool any = false;
+  for (size_t p = 0; p < n_pairs; ++p)
+    if (xi[p] < X.n && yi[p] < Y.n && qg_pair_is_sparse (cfg, X.len (xi[p]), Y.len (yi[p]))) { any = true; ymax = std::max (ymax, Y.len (yi[p])); }
+  if (!any) return false;
+  if (getenv ("QG_SEED_GENERAL")) return true;                 // tests: force the general path
+  const int k = cfg->kmer_len;
+  return k < 5 || k > 7 || ymax > 65000 || qg_seed_smem_bytes (k, ymax, nullptr) > ctx->smem_optin;
+}
+
+// per-read sorted (k-mer, start position) index for the general path; keys/vals end up in SC_KEYS1 / SC_VALS1
+static int qg_build_read_index (qg_ctx* ctx, int k, const std::vector<qg_index_job>& jobs, uint64_t total) {
+  qg_seqset& Y = ctx->seqs[QG_READS];
+  QG_TRY (qg_reserve (ctx, ctx->scratch[SC_YC64], sizeof (unsigned long long) * (Y.total + 1)));
+  QG_LAUNCH (qg_codes64_kernel, (unsigned) ((Y.total + 255) / 256), 256, 0, ctx->stream,
+             Y.d_tok.as<uint8_t> (), Y.d_off.as<uint64_t> (), (uint32_t) Y.n, Y.total, k, ctx->scratch[SC_YC64].as<unsigned long long> ());
+  QG_TRY (qg_check_launch (ctx, "qg_codes64_kernel"));
+  QG_TRY (qg_upload (ctx, ctx->scratch[SC_IDXJOBS], jobs.data (), sizeof (qg_index_job) * jobs.size ()));
+  for (int b = SC_KEYS0; b <= SC_KEYS1; ++b) QG_TRY (qg_reserve (ctx, ctx->scratch[b], sizeof (unsigned long long) * (total + 1)));
+  for (int b = SC_VALS0; b <= SC_VALS1; ++b) QG_TRY (qg_reserve (ctx, ctx->scratch[b], sizeof (uint32_t) * (total + 1)));
+  uint32_t nmax = 0;
+  std::vector<uint32_t> segoff (2 * jobs.size ());
+  for (size_t t = 0; t < jobs.size (); ++t) { nmax = std::max (nmax, jobs[t].n); segoff[t] = (uint32_t) jobs[t].idx_off; segoff[jobs.size () + t] = (uint32_t) (jobs[t].idx_off + jobs[t].n); }
+  QG_TRY (qg_upload (ctx, ctx->scratch[SC_SEGOFF], segoff.data (), sizeof (uint32_t) * segoff.size ()));
+  dim3 grid ((nmax + 255) / 256, (unsigned) jobs.size ());
+  QG_LAUNCH (qg_index_fill_kernel, grid, 256, 0, ctx->stream, ctx->scratch[SC_IDXJOBS].as<qg_index_job> (),
+             ctx->scratch[SC_YC64].as<unsigned long long> (), ctx->scratch[SC_KEYS0].as<unsigned long long> (), ctx->scratch[SC_VALS0].as<uint32_t> ());
+  QG_TRY (qg_check_launch (ctx, "qg_index_fill_kernel"));
+#ifdef QG_EMU
+  QG_CUDA (ctx, cudaStreamSynchronize (ctx->stream));
+  {
+    const unsigned long long* k0 = ctx->scratch[SC_KEYS0].as<unsigned long long> (); const uint32_t* v0 = ctx->scratch[SC_VALS0].as<uint32_t> ();
+    unsigned long long* k1 = ctx->scratch[SC_KEYS1].as<unsigned long long> (); uint32_t* v1 = ctx->scratch[SC_VALS1].as<uint32_t> ();
+    for (const qg_index_job& jb : jobs) {
+      std::vector<uint32_t> perm (jb.n);
+      for (uint32_t j = 0; j < jb.n; ++j) perm[j] = j;
+      std::stable_sort (perm.begin (), perm.end (), [&] (uint32_t a, uint32_t b) { return k0[jb.idx_off + a] < k0[jb.idx_off + b]; });
+      for (uint32_t j = 0; j < jb.n; ++j) { k1[jb.idx_off + j] = k0[jb.idx_off + perm[j]]; v1[jb.idx_off + j] = v0[jb.idx_off + perm[j]]; }
+    }
+  }
+#else
+  {
+    const uint32_t* segb = ctx->scratch[SC_SEGOFF].as<uint32_t> ();
+    const uint32_t* sege = segb + jobs.size ();
+    size_t tmp = 0;
+    QG_CUDA (ctx, cub::DeviceSegmentedRadixSort::SortPairs (nullptr, tmp, ctx->scratch[SC_KEYS0].as<unsigned long long> (), ctx->scratch[SC_KEYS1].as<unsigned long long> (),
+                  ctx->scratch[SC_VALS0].as<uint32_t> (), ctx->scratch[SC_VALS1].as<uint32_t> (), (int) total, (int) jobs.size (), segb, sege, 0, 2 * k, ctx->stream));
+    QG_TRY (qg_reserve (ctx, ctx->scratch[SC_SORTTMP], tmp + 16));
+    QG_CUDA (ctx, cub::DeviceSegmentedRadixSort::SortPairs (ctx->scratch[SC_SORTTMP].p, tmp, ctx->scratch[SC_KEYS0].as<unsigned long long> (), ctx->scratch[SC_KEYS1].as<unsigned long long> (),
+                  ctx->scratch[SC_VALS0].as<uint32_t> (), ctx->scratch[SC_VALS1].as<uint32_t> (), (int) total, (int) jobs.size (), segb, sege, 0, 2 * k, ctx->stream));
+  }
+#endif
+  return QG_OK;
+}
+
 static int qg_envelope_stage_cap (qg_ctx* ctx, const qg_dpconfig* cfg, uint64_t cell_size, int x_set,
                                   size_t n_pairs, const uint32_t* xi, const uint32_t* yi, qg_env_result& out, uint32_t run_cap, bool* overflow) {
   *overflow = false;
@@ -307,6 +385,10 @@ static int qg_envelope_stage_cap (qg_ctx* ctx, const qg_dpconfig* cfg, uint64_t 
   chunk = std::max<int64_t> (QG_SEED_CHUNK, std::min<int64_t> (chunk, 8 * QG_SEED_CHUNK));
   chunk = (chunk / QG_SEED_STEP) * QG_SEED_STEP;
   const bool memory_mode = cfg->kmer_threshold < 0;
+  if (cfg->sparse && (k < 1 || k > 32)) QG_FAIL (ctx, QG_ERR_INVALID, "-kmatch %d: k-mer length must be 1..32", k);
+  const bool general = qg_seed_is_general (ctx, cfg, x_set, n_pairs, xi, yi);
+  const int64_t gen_chunk = 32768;                               // reference positions per work item on the general path
+  std::vector<qg_index_job> idx_jobs; std::map<uint32_t, uint64_t> idx_of_read; uint64_t idx_total = 0;
   std::vector<uint32_t> mem_pairs;
   uint64_t count_total = 0, bits_total = 0, hist_total = 0;
   uint32_t ymax = 0;
@@ -317,28 +399,40 @@ static int qg_envelope_stage_cap (qg_ctx* ctx, const qg_dpconfig* cfg, uint64_t 
     d.xseq = xi[p]; d.yseq = yi[p]; d.xlen = X.len (xi[p]); d.ylen = Y.len (yi[p]);
     d.xoff = X.off[xi[p]]; d.yoff = Y.off[yi[p]];
     if (d.xlen == 0 || d.ylen == 0) QG_FAIL (ctx, QG_ERR_INVALID, "pair %zu: empty sequence", p);
-    bool full = !cfg->sparse;
-    if (!full && cfg->kmer_threshold >= 0) {                    // diagenv.cpp:23-29
-      const uint32_t min_len = 2u * (uint32_t) (k + cfg->kmer_threshold);
-      if (d.xlen < min_len || d.ylen < min_len) full = true;
-    }
+    const bool full = !qg_pair_is_sparse (cfg, d.xlen, d.ylen);
     d.full = full ? 1 : 0;
+    d.idx_off = 0;
     d.item_begin = (uint32_t) items.size ();
     d.run_cap = 0; d.pad_ = 0; d.count_off = 0; d.bits_off = 0; d.hist_off = 0;
     uint64_t runs_here = 1;
     if (!full) {
       if (d.xlen < (uint32_t) k || d.ylen < (uint32_t) k)
         QG_FAIL (ctx, QG_ERR_PRECONDITION, "pair %zu: sequence shorter than k=%d (the reference's KmerIndex underflows here, fastseq.cpp:247)", p, k);
-      if (d.ylen > 65000) QG_FAIL (ctx, QG_ERR_UNSUPPORTED, "pair %zu: read of %u bases exceeds the 16-bit bucket index of the seeding kernel", p, d.ylen);
       any_sparse = true;
       ymax = std::max (ymax, d.ylen);
-      const int64_t dmin = -((int64_t) d.ylen - k), dmax = (int64_t) d.xlen - k;   // diagonals that can receive hits
-      for (int64_t b = dmin; b <= dmax; b += chunk) {
-        qg_seed_item it; it.pair = (uint32_t) p; it.d_begin = (int32_t) b; it.d_end = (int32_t) std::min<int64_t> (b + chunk, dmax + 1);
-        items.push_back (it);
+      if (general) {
+        for (int64_t b = 0; b <= (int64_t) d.xlen - k; b += gen_chunk) {           // items over reference positions
+          qg_seed_item it; it.pair = (uint32_t) p; it.d_begin = (int32_t) b; it.d_end = (int32_t) std::min<int64_t> (b + gen_chunk, (int64_t) d.xlen - k + 1);
+          items.push_back (it);
+        }
+        auto f = idx_of_read.find (d.yseq);
+        if (f == idx_of_read.end ()) {
+          qg_index_job jb; jb.yoff = d.yoff; jb.idx_off = idx_total; jb.n = d.ylen - (uint32_t) k + 1; jb.pad_ = 0;
+          idx_jobs.push_back (jb);
+          f = idx_of_read.insert (std::make_pair (d.yseq, idx_total)).first;
+          idx_total += jb.n;
+          if (idx_total > 0x7FFFFFF0ull) QG_FAIL (ctx, QG_ERR_UNSUPPORTED, "read index of one seeding batch exceeds 2^31 k-mers; split the pair list");
+        }
+        d.idx_off = f->second;
+      } else {
+        const int64_t dmin = -((int64_t) d.ylen - k), dmax = (int64_t) d.xlen - k;   // diagonals that can receive hits
+        for (int64_t b = dmin; b <= dmax; b += chunk) {
+          qg_seed_item it; it.pair = (uint32_t) p; it.d_begin = (int32_t) b; it.d_end = (int32_t) std::min<int64_t> (b + chunk, dmax + 1);
+          items.push_back (it);
+        }
       }
       runs_here = (uint64_t) (items.size () - d.item_begin) * run_cap + 1;
-      if (memory_mode) {
+      if (memory_mode || general) {
         d.full = 2;
         mem_pairs.push_back ((uint32_t) p);
         d.count_off = count_total; count_total += (uint64_t) d.xlen + d.ylen;
@@ -353,13 +447,12 @@ static int qg_envelope_stage_cap (qg_ctx* ctx, const qg_dpconfig* cfg, uint64_t 
     run_total += runs_here;
     if (run_total > 0xFFFFFFF0ull) QG_FAIL (ctx, QG_ERR_UNSUPPORTED, "too many seeding work items in one call; split the pair list");
   }
-  if (any_sparse && (k < 5 || k > 7)) QG_FAIL (ctx, QG_ERR_UNSUPPORTED, "-kmatch %d: this build's seeding kernel indexes k-mers of length 5..7 in shared memory", k);
 
   qg_dbuf &dPD = ctx->scratch[SC_PAIRDESC], &dIT = ctx->scratch[SC_ITEMS], &dIR = ctx->scratch[SC_ITEMRUNS], &dIN = ctx->scratch[SC_ITEMNRUNS];
   qg_dbuf &dPR = ctx->scratch[SC_PAIRRUNS], &dPI = ctx->scratch[SC_PAIRINFO], &dPC = ctx->scratch[SC_PAIRCU], &dFL = ctx->scratch[SC_FLAGS];
   QG_TRY (qg_upload (ctx, dPD, pd.data (), sizeof (qg_pair_desc) * n_pairs));
   QG_TRY (qg_upload (ctx, dIT, items.data (), sizeof (qg_seed_item) * items.size ()));
-  QG_TRY (qg_reserve (ctx, dIR, sizeof (int2) * (items.size () * run_cap + 1)));
+  QG_TRY (qg_reserve (ctx, dIR, sizeof (int2) * ((general ? 0 : items.size () * run_cap) + 1)));
   QG_TRY (qg_reserve (ctx, dIN, sizeof (uint32_t) * (items.size () + 1)));
   QG_TRY (qg_reserve (ctx, dPR, sizeof (int2) * (run_total + 1)));
   QG_TRY (qg_reserve (ctx, dPI, sizeof (uint2) * (n_pairs + 1)));
@@ -367,22 +460,35 @@ static int qg_envelope_stage_cap (qg_ctx* ctx, const qg_dpconfig* cfg, uint64_t 
   QG_TRY (qg_reserve (ctx, dFL, 64));
   QG_CUDA (ctx, cudaMemsetAsync (dFL.p, 0, 64, ctx->stream));
 
-  if (memory_mode && !mem_pairs.empty ()) {
+  if ((memory_mode || general) && !mem_pairs.empty ()) {
     QG_TRY (qg_reserve (ctx, ctx->scratch[SC_STORE], sizeof (uint32_t) * (count_total + 1)));
     QG_TRY (qg_reserve (ctx, ctx->scratch[SC_ROWACC], sizeof (uint32_t) * (hist_total + 1)));
     QG_TRY (qg_reserve (ctx, ctx->scratch[SC_MISC1], sizeof (uint32_t) * (bits_total + 1)));
     QG_TRY (qg_upload (ctx, ctx->scratch[SC_MISC0], mem_pairs.data (), sizeof (uint32_t) * mem_pairs.size ()));
     QG_CUDA (ctx, cudaMemsetAsync (ctx->scratch[SC_STORE].p, 0, sizeof (uint32_t) * (count_total + 1), ctx->stream));
   }
+  if (!items.empty () && general) {
+    qg_seqset& XS = ctx->seqs[x_set];
+    qg_timer tm (ctx, &ctx->stats.ms_seed);
+    QG_TRY (qg_build_read_index (ctx, k, idx_jobs, idx_total));
+    QG_TRY (qg_reserve (ctx, ctx->scratch[SC_XC64], sizeof (unsigned long long) * (XS.total + 1)));
+    QG_LAUNCH (qg_codes64_kernel, (unsigned) ((XS.total + 255) / 256), 256, 0, ctx->stream,
+               XS.d_tok.as<uint8_t> (), XS.d_off.as<uint64_t> (), (uint32_t) XS.n, XS.total, k, ctx->scratch[SC_XC64].as<unsigned long long> ());
+    QG_TRY (qg_check_launch (ctx, "qg_codes64_kernel"));
+    QG_LAUNCH (qg_seed_general_kernel, (unsigned) items.size (), 256, 0, ctx->stream,
+               dIT.as<qg_seed_item> (), dPD.as<qg_pair_desc> (), ctx->scratch[SC_XC64].as<unsigned long long> (),
+               ctx->scratch[SC_KEYS1].as<unsigned long long> (), ctx->scratch[SC_VALS1].as<uint32_t> (), k,
+               ctx->scratch[SC_STORE].as<uint32_t> (), (unsigned long long*) ((char*) dFL.p + 8));
+    QG_TRY (qg_check_launch (ctx, "qg_seed_general_kernel"));
+  }
   if (!items.empty ()) {
+    if (!general) {
     QG_TRY (qg_ensure_codes (ctx, x_set, k));
     QG_TRY (qg_ensure_codes (ctx, QG_READS, k));
-    const uint32_t nk = 1u << (2 * k);
-    uint32_t need = std::max<uint32_t> (nk, QG_SEED_STEP + ymax + 1), ring = 1;
-    while (ring < need) ring <<= 1;
-    const size_t smem = (size_t) ring * 4 + (size_t) nk * 4 + (size_t) ((ymax + 2) & ~1u) * 2 + (QG_SEED_STEP / 32 + 2) * 4;
+    uint32_t ring = 1;
+    const size_t smem = qg_seed_smem_bytes (k, ymax, &ring);
     if (smem > ctx->smem_optin)
-      QG_FAIL (ctx, QG_ERR_UNSUPPORTED, "reads of up to %u bases need %zu B of shared memory per seeding CTA (limit %zu)", ymax, smem, ctx->smem_optin);
+      QG_FAIL (ctx, QG_ERR_CUDA, "internal: seeding kernel selection (%zu B of shared memory needed, limit %zu)", smem, ctx->smem_optin);
     QG_CUDA (ctx, cudaFuncSetAttribute (qg_seed_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
     QG_CUDA (ctx, cudaFuncSetAttribute (qg_seed_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
     {
@@ -395,12 +501,13 @@ static int qg_envelope_stage_cap (qg_ctx* ctx, const qg_dpconfig* cfg, uint64_t 
                  memory_mode ? ctx->scratch[SC_STORE].as<uint32_t> () : (uint32_t*) nullptr);
       QG_TRY (qg_check_launch (ctx, "qg_seed_kernel"));
     }
-    if (memory_mode) {
+    }
+    if (memory_mode || general) {
       qg_timer tm (ctx, &ctx->stats.ms_envelope);
       QG_LAUNCH (qg_memtier_kernel, (unsigned) mem_pairs.size (), 256, 0, ctx->stream,
                  dPD.as<qg_pair_desc> (), ctx->scratch[SC_MISC0].as<uint32_t> (), ctx->scratch[SC_STORE].as<uint32_t> (),
                  ctx->scratch[SC_ROWACC].as<uint32_t> (), ctx->scratch[SC_MISC1].as<uint32_t> (), k, (int) ((unsigned) cfg->band_size / 2),
-                 (unsigned long long) cell_size, (unsigned long long) cfg->max_size,
+                 memory_mode ? -1 : cfg->kmer_threshold, (unsigned long long) cell_size, (unsigned long long) cfg->max_size,
                  dPR.as<int2> (), dPI.as<uint2> (), (uint32_t*) dFL.p);
       QG_TRY (qg_check_launch (ctx, "qg_memtier_kernel"));
     }
@@ -443,8 +550,8 @@ static int qg_envelope_stage_cap (qg_ctx* ctx, const qg_dpconfig* cfg, uint64_t 
 
 // run buffers are sized for the common case (a handful of runs per 192k-diagonal chunk) and grown on demand up
 // to the most runs a chunk can hold, chunk / (band + 2) + 2
-static int qg_envelope_stage (qg_ctx* ctx, const qg_dpconfig* cfg, uint64_t cell_size, int x_set,
-                              size_t n_pairs, const uint32_t* xi, const uint32_t* yi, qg_env_result& out) {
+static int qg_envelope_stage_retry (qg_ctx* ctx, const qg_dpconfig* cfg, uint64_t cell_size, int x_set,
+                                    size_t n_pairs, const uint32_t* xi, const uint32_t* yi, qg_env_result& out) {
   const uint32_t half = (uint32_t) cfg->band_size / 2;
   const uint32_t cap_max = 8 * QG_SEED_CHUNK / (2 * half + 2) + 3;
   uint32_t cap = (uint32_t) qg_env_size ("QG_RUN_CAP", 64);
@@ -455,6 +562,40 @@ static int qg_envelope_stage (qg_ctx* ctx, const qg_dpconfig* cfg, uint64_t cell
     if (cap >= cap_max) QG_FAIL (ctx, QG_ERR_CUDA, "internal: run buffer overflow at the theoretical maximum of %u runs per chunk", cap);
     cap = std::min<uint64_t> ((uint64_t) cap * 16, cap_max);
   }
+}
+
+// The memory-guided mode and the general seeding path keep one 32-bit counter per diagonal per pair in HBM: the pair
+// list is cut into sub-batches whose counters fit the budget.
+static int qg_envelope_stage (qg_ctx* ctx, const qg_dpconfig* cfg, uint64_t cell_size, int x_set,
+                              size_t n_pairs, const uint32_t* xi, const uint32_t* yi, qg_env_result& out) {
+  const bool counters = cfg->sparse && (cfg->kmer_threshold < 0 || qg_seed_is_general (ctx, cfg, x_set, n_pairs, xi, yi));
+  if (!counters) return qg_envelope_stage_retry (ctx, cfg, cell_size, x_set, n_pairs, xi, yi, out);
+  const qg_seqset& X = ctx->seqs[x_set];
+  const qg_seqset& Y = ctx->seqs[QG_READS];
+  size_t freeb = 0, totb = 0;
+  QG_CUDA (ctx, cudaMemGetInfo (&freeb, &totb));
+  const uint64_t budget = (uint64_t) qg_env_size ("QG_COUNT_BUDGET_MB", std::min<size_t> (freeb / 3, (size_t) 16 << 30) >> 20) << 20;
+  out = qg_env_result ();
+  out.run_begin.push_back (0);
+  size_t p0 = 0;
+  while (p0 < n_pairs) {
+    size_t p1 = p0; uint64_t bytes = 0, kmers = 0;
+    while (p1 < n_pairs) {
+      if (xi[p1] >= X.n || yi[p1] >= Y.n) QG_FAIL (ctx, QG_ERR_INVALID, "pair %zu: sequence index out of range", p1);
+      const uint64_t need = ((uint64_t) X.len (xi[p1]) + Y.len (yi[p1])) * 5 + 64;     // counters + three bitmaps + count histogram
+      if (p1 > p0 && (bytes + need > budget || kmers + Y.len (yi[p1]) > 0x40000000ull)) break;
+      bytes += need; kmers += Y.len (yi[p1]); ++p1;
+    }
+    qg_env_result part;
+    QG_TRY (qg_envelope_stage_retry (ctx, cfg, cell_size, x_set, p1 - p0, xi + p0, yi + p0, part));
+    for (size_t p = 0; p < p1 - p0; ++p) {
+      for (uint32_t r = part.run_begin[p]; r < part.run_begin[p + 1]; ++r) out.runs.push_back (part.runs[r]);
+      out.run_begin.push_back ((uint32_t) out.runs.size ());
+      out.cu.push_back (part.cu[p]); out.ndiag.push_back (part.ndiag[p]);
+    }
+    p0 = p1;
+  }
+  return QG_OK;
 }
 
 extern "C" int qg_envelopes (qg_ctx* ctx, const qg_dpconfig* cfg, uint64_t cell_size, int x_set,
@@ -639,26 +780,27 @@ static int qg_wide_run (qg_ctx* ctx, const qg_dpconfig* cfg, const qg_env_result
     // ---- plan a batch of pairs under the memory budget
     std::vector<qg_wseg> segs; std::vector<qg_tile> tiles; std::vector<qg_wpair> wp; std::vector<long long> tables;
     qg_dp_plan rpplan; std::map<uint32_t, uint64_t> rp_of_read;
-    uint64_t trace_words = 0, col_d = 0, row_d = 0, end_d = 0, bytes = 0, scratch_bytes = 0;
+    uint64_t end_d = 0, bytes = 0, scratch_bytes = 0;
+    const uint64_t tile_bytes = (mode == 0 ? QG_TILE_WORDS * 4ull : 0) + (QG_TRH + QG_TCW) * 24ull + 2 * 16 + sizeof (qg_tile);
     size_t q1 = q0;
     while (q1 < idx.size ()) {
       const size_t p = idx[q1];
       const uint32_t xlen = X.len (xi[p]), ylen = Y.len (yi[p]);
       const uint32_t nCB = (xlen + QG_TCW - 1) / QG_TCW, nRB = (ylen + QG_TRH - 1) / QG_TRH;
-      // count tiles of this pair first
+      // tiles a run touches in row block b: columns [jLo + dlo, jHi + dhi] clipped to [1, xLen]
+      auto col_blocks = [&] (int dlo, int dhi, uint32_t b, int64_t* aLo, int64_t* aHi) {
+        const int64_t jLo = (int64_t) b * QG_TRH + 1, jHi = std::min<int64_t> ((int64_t) (b + 1) * QG_TRH, ylen);
+        const int64_t iLo = std::max<int64_t> (1, jLo + dlo), iHi = std::min<int64_t> (xlen, jHi + dhi);
+        if (iLo > iHi) { *aLo = 0; *aHi = -1; return; }
+        *aLo = (iLo - 1) / QG_TCW; *aHi = (iHi - 1) / QG_TCW;
+      };
       uint64_t ntile = 0;
       for (uint32_t r = er.run_begin[p]; r < er.run_begin[p + 1]; ++r)
-        for (uint32_t a = 0; a < nCB; ++a)
-          for (uint32_t b = 0; b < nRB; ++b) {
-            const int64_t iLo = (int64_t) a * QG_TCW + 1, iHi = std::min<int64_t> ((int64_t) (a + 1) * QG_TCW, xlen);
-            const int64_t jLo = (int64_t) b * QG_TRH + 1, jHi = std::min<int64_t> ((int64_t) (b + 1) * QG_TRH, ylen);
-            if (iHi - jLo >= er.runs[r].x && iLo - jHi <= er.runs[r].y) ++ntile;
-          }
+        for (uint32_t b = 0; b < nRB; ++b) { int64_t aLo, aHi; col_blocks (er.runs[r].x, er.runs[r].y, b, &aLo, &aHi); ntile += (uint64_t) (aHi - aLo + 1); }
       const uint64_t nruns = er.run_begin[p + 1] - er.run_begin[p];
-      const uint64_t need = ntile * (mode == 0 ? QG_TILE_WORDS * 4ull : 0) + nruns * (((uint64_t) nCB + 1) * (ylen + 1) + ((uint64_t) nRB + 1) * (xlen + 1)) * 24
-                            + nruns * (uint64_t) nCB * nRB * 8 + (uint64_t) (xlen + 1) * 8 * nruns;
-      if (q1 > q0 && bytes + need > budget) break;
-      if (need > budget) QG_FAIL (ctx, QG_ERR_UNSUPPORTED, "pair %zu needs %llu MB of device memory for its %llu tiles (budget %llu MB)", p,
+      const uint64_t need = ntile * tile_bytes + nruns * ((uint64_t) nCB * nRB * 8 + (uint64_t) (xlen + 1) * 8) + 2ull * (xlen + ylen);
+      if (q1 > q0 && (bytes + need > budget || tiles.size () + ntile > 0x7FFFFFF0ull)) break;
+      if (need > budget || ntile > 0x7FFFFFF0ull) QG_FAIL (ctx, QG_ERR_UNSUPPORTED, "pair %zu needs %llu MB of device memory for its %llu tiles (budget %llu MB)", p,
                                   (unsigned long long) (need >> 20), (unsigned long long) ntile, (unsigned long long) (budget >> 20));
       bytes += need;
       qg_wpair w; memset (&w, 0, sizeof (w));
@@ -675,20 +817,20 @@ static int qg_wide_run (qg_ctx* ctx, const qg_dpconfig* cfg, const qg_env_result
         qg_wseg ws; memset (&ws, 0, sizeof (ws));
         ws.pair = (uint32_t) wp.size (); ws.xseq = xi[p]; ws.xlen = xlen; ws.ylen = ylen; ws.dlo = er.runs[r].x; ws.dhi = er.runs[r].y;
         ws.nCB = nCB; ws.nRB = nRB; ws.rp_off = it->second;
-        ws.col_off = col_d; col_d += ((uint64_t) nCB + 1) * (ylen + 1) * 3;
-        ws.row_off = row_d; row_d += ((uint64_t) nRB + 1) * (xlen + 1) * 3;
         ws.table_off = tables.size (); tables.resize (tables.size () + (size_t) nCB * nRB, -1);
         ws.end_off = end_d; end_d += (uint64_t) xlen + 1;
-        for (uint32_t a = 0; a < nCB; ++a)
-          for (uint32_t b = 0; b < nRB; ++b) {
-            const int64_t iLo = (int64_t) a * QG_TCW + 1, iHi = std::min<int64_t> ((int64_t) (a + 1) * QG_TCW, xlen);
-            const int64_t jLo = (int64_t) b * QG_TRH + 1, jHi = std::min<int64_t> ((int64_t) (b + 1) * QG_TRH, ylen);
-            if (!(iHi - jLo >= ws.dlo && iLo - jHi <= ws.dhi)) continue;
-            qg_tile t; t.seg = (uint32_t) segs.size (); t.a = a; t.b = b; t.id = (uint32_t) tiles.size (); t.trace_off = trace_words;
-            tables[ws.table_off + (size_t) a * nRB + b] = (long long) trace_words;
-            if (mode == 0) trace_words += QG_TILE_WORDS;
+        long long* tab = tables.data () + ws.table_off;
+        for (uint32_t b = 0; b < nRB; ++b) {
+          int64_t aLo, aHi; col_blocks (ws.dlo, ws.dhi, b, &aLo, &aHi);
+          for (int64_t a = aLo; a <= aHi; ++a) {
+            qg_tile t; t.seg = (uint32_t) segs.size (); t.a = (uint32_t) a; t.b = b; t.id = (uint32_t) tiles.size (); t.pad_ = 0;
+            t.left = a > 0 ? (int32_t) tab[(size_t) (a - 1) * nRB + b] : -1;
+            t.up = b > 0 ? (int32_t) tab[(size_t) a * nRB + (b - 1)] : -1;
+            t.diag = (a > 0 && b > 0) ? (int32_t) tab[(size_t) (a - 1) * nRB + (b - 1)] : -1;
+            tab[(size_t) a * nRB + b] = (long long) t.id;
             tiles.push_back (t);
           }
+        }
         segs.push_back (ws);
         if (first) { dmin = ws.dlo; dmax = ws.dhi; first = false; } else { dmin = std::min (dmin, ws.dlo); dmax = std::max (dmax, ws.dhi); }
       }
@@ -701,6 +843,8 @@ static int qg_wide_run (qg_ctx* ctx, const qg_dpconfig* cfg, const qg_env_result
       wp.push_back (w);
       ++q1;
     }
+    const uint64_t trace_words = mode == 0 ? (uint64_t) tiles.size () * QG_TILE_WORDS : 0;
+    const uint64_t col_d = (uint64_t) tiles.size () * QG_TRH * 3, row_d = (uint64_t) tiles.size () * QG_TCW * 3;
     const size_t np = wp.size ();
     // tiles in wavefront order
     std::vector<qg_tile> sorted (tiles);

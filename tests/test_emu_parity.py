@@ -129,3 +129,18 @@ def test_emu_wide_runs_tiled(emu_lib, oracle, monkeypatch):
             pc.check_forward(g, oracle, x, reads, s_or, cfg, xi, yi)
     finally:
         g.close()
+
+
+def test_emu_general_seeding_path(emu, oracle, workload, monkeypatch):
+    """k-mer lengths outside the shared-memory kernel's 5..7 (and reads too long for it) take the general path:
+    sorted read index + per-diagonal counters in HBM.  Envelopes stay bit-exact, in both threshold modes."""
+    x, reads, _ = workload
+    xi, yi = pc.all_pairs(len(x), len(reads))
+    for k, thr in ((4, 30), (8, 4), (11, 2), (3, 60)):
+        pc.check_envelopes(emu, oracle, x, reads, api.dp_config(kmer_len=k, kmer_threshold=thr), xi, yi)
+    pc.check_envelopes(emu, oracle, x, reads, api.dp_config(kmer_len=9, kmer_threshold=-1, max_size=400_000), xi, yi)
+    monkeypatch.setenv("QG_SEED_GENERAL", "1")
+    pc.check_envelopes(emu, oracle, x, reads, api.dp_config(kmer_threshold=6), xi, yi)
+    pc.check_envelopes(emu, oracle, x, reads, api.dp_config(kmer_threshold=-1, max_size=300_000), xi, yi)
+    monkeypatch.setenv("QG_COUNT_BUDGET_MB", "0")     # one pair per sub-batch
+    pc.check_envelopes(emu, oracle, x, reads, api.dp_config(kmer_threshold=6), xi, yi)

@@ -195,3 +195,28 @@ def test_wide_and_narrow_pairs_mixed(gpu, oracle, workload, monkeypatch):
     for p0, p1 in zip(a0["paths"], a1["paths"]):
         assert np.array_equal(p0, p1)
     assert np.isfinite(f1).any()
+
+
+def test_general_seeding_path(gpu, oracle, workload, monkeypatch):
+    """-kmatch k outside 5..7 and reads beyond the shared-memory kernel's reach: sorted read index (CUB segmented
+    radix sort) + HBM counters; envelopes bit-exact, then Viterbi on top of them"""
+    x, reads, s_or = workload
+    xi, yi = pc.all_pairs(len(x), len(reads))
+    for k, thr in ((4, 60), (8, 6), (12, 3), (20, 1), (32, 1)):
+        pc.check_envelopes(gpu, oracle, x, reads, api.dp_config(kmer_len=k, kmer_threshold=thr), xi, yi)
+    pc.check_envelopes(gpu, oracle, x, reads, api.dp_config(kmer_len=9, kmer_threshold=-1, max_size=20_000_000), xi, yi)
+    pc.check_viterbi(gpu, oracle, x, reads, s_or, api.dp_config(kmer_len=10, kmer_threshold=4), xi, yi)
+    monkeypatch.setenv("QG_SEED_GENERAL", "1")
+    pc.check_envelopes(gpu, oracle, x, reads, api.dp_config(kmer_threshold=14), xi, yi)
+    monkeypatch.setenv("QG_COUNT_BUDGET_MB", "1")
+    pc.check_envelopes(gpu, oracle, x, reads, api.dp_config(kmer_threshold=14), xi, yi)
+
+
+def test_long_read_seeding(gpu, oracle):
+    """a 70 kb read does not fit the shared-memory index: general path, bit-exact envelope"""
+    x, reads = pc.make_workload(ref_len=200000, n_reads=1, read_len=70000, seed=31)
+    gpu.set_refs(x); gpu.set_reads(reads); gpu.set_params(pc.default_params())
+    xi, yi = pc.all_pairs(len(x), len(reads))
+    pc.check_envelopes(gpu, oracle, x, reads, api.dp_config(), xi, yi)
+    v = gpu.viterbi(api.dp_config(), xi, yi)
+    assert np.isfinite(v["score"]).any()
