@@ -325,18 +325,42 @@ def main():
         # chunk overlap) ; the Viterbi fill writes 4 B of pointers per lane and macro-step (= trace_bytes)
         seed_bytes = 2.0 * (args.ref_len * 2) * iso_reads
         vit_bytes = float(sums[6]) / world
-        roofline = {
+        # DRAM traffic of the dominant kernel per launch, from the committed ncu --set full capture of this same workload
+        traffic = None
+        try:
+            tj = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01c_traffic.json")))
+            w = tj["workload"]
+            if (w["reads_per_launch"], w["ref_len"], w["read_len"]) == (iso_reads // n_iso, args.ref_len, args.read_len):
+                k = tj["qg_seed_kernel" if seed_dom else "qg_fill_kernel<3,0,0>"]
+                traffic = k["dram_bytes_read"] + k["dram_bytes_write"]
+        except Exception:
+            traffic = None
+        seed_gbps = seed_bytes / (ms_seed / 1e3) / 1e9
+        vit_gbps = vit_bytes / (ms_vit / 1e3) / 1e9
+        compute = {
             "kernel": "qg_seed_kernel" if seed_dom else "qg_fill_kernel<R,Viterbi>",
             "bound": "smem_atomic" if seed_dom else "fp64_issue",
             "achieved": seed_hps / 1e9 if seed_dom else vit_cups / 1e9,
             "peak": PEAK_SMEM_ATOMIC / 1e9 if seed_dom else PEAK_LANE_INSTR / INSTR_PER_CU["viterbi"] / 1e9,
             "unit": "Ghit/s" if seed_dom else "GCUPS",
             "frac": (seed_hps / PEAK_SMEM_ATOMIC) if seed_dom else vit_cups / (PEAK_LANE_INSTR / INSTR_PER_CU["viterbi"]),
-            "traffic": None,
-            "definition": "SURVEY.md 8d / DESIGN.md: neither kernel is HBM- or tensor-bound; peaks are the shared-memory atomic issue "
-                          "rate (148 SM x 32 lanes x 1965 MHz) and 148 x 128 x 1965 MHz lane-instructions/s over 13 instr per cell update",
-            "hbm": {"seed_GBps": seed_bytes / (ms_seed / 1e3) / 1e9, "viterbi_trace_GBps": vit_bytes / (ms_vit / 1e3) / 1e9,
-                    "peak_GBps": hbm_peak, "peak_source": peak_src},
+            "definition": "SURVEY.md 8d / DESIGN.md 4.1: the dominant kernel is bound by shared-memory atomics / instruction issue, not by HBM or tensor "
+                          "cores; peaks are the shared-memory atomic issue rate (148 SM x 32 lanes x 1965 MHz) and 148 x 128 x 1965 MHz "
+                          "lane-instructions/s over 13 instr per cell update",
+        }
+        roofline = {
+            "kernel": compute["kernel"],
+            "bound": "hbm",
+            "achieved": seed_gbps if seed_dom else vit_gbps,
+            "peak": hbm_peak, "unit": "GB/s",
+            "frac": (seed_gbps if seed_dom else vit_gbps) / hbm_peak,
+            "traffic": traffic,
+            "peak_source": peak_src,
+            "algorithmic_bytes": "seeding: 2 B k-mer code per reference position per pair-strand (DESIGN.md 4.1); Viterbi: 4 B of pointers per lane and macro-step",
+            "note": "the HBM view the contract asks for; DRAM traffic is far below the algorithmic bytes because the code stream is served by L2. "
+                    "The kernel's real limiter is in `compute`",
+            "compute": compute,
+            "hbm": {"seed_GBps": seed_gbps, "viterbi_trace_GBps": vit_gbps, "peak_GBps": hbm_peak, "peak_source": peak_src},
             "all": {"seed_ghits_s": seed_hps / 1e9, "seed_frac_of_smem_atomic_peak": seed_hps / PEAK_SMEM_ATOMIC,
                     "viterbi_gcups": vit_cups / 1e9, "viterbi_frac_of_fp32_roofline": vit_cups / (PEAK_LANE_INSTR / INSTR_PER_CU["viterbi"]),
                     "viterbi_frac_of_fp64_roofline": vit_cups / (PEAK_LANE_INSTR / 2 / INSTR_PER_CU["viterbi"]),

@@ -26,6 +26,7 @@ def _worker(rank, world, port, emu_lib, q):
     nullp = QuaffNullParams.load(os.path.join(ROOT, "tests", "golden", "testquaffnullparams.json"))
     G = api.QuaffGPU(lib_path=emu_lib)
     G.set_refs(x); G.set_params(qp)
+    G.set_fb_exact(True)          # log-space kernels: per-read log-likelihoods bit-identical to the oracle
     null_ll = np.array([api.null_loglike(nullp, r, G.L) for r in reads])
     r = qd.distributed_estep(G, api.dp_config(kmer_threshold=6), reads, True, null_ll)
     q.put((rank, r["counts"], r["loglike"], r["shard"], list(r["y_loglike"])))
