@@ -109,7 +109,7 @@ def test_cli_dropin_emulated(tmp_path, emu_lib):
     if not os.path.exists(REFQ) or not os.path.isdir("/root/reference/src"):
         pytest.skip("reference CLI not built here")
     subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "host"), "all", "emu"])
-    _compare_all(EMUQ, str(tmp_path), dict(align=(3000, 3, 300, 5), overlap=(600, 4, 420, 15)), kn=6, same_libm=True)
+    _compare_all(EMUQ, str(tmp_path), dict(align=(2000, 2, 200, 5), overlap=(500, 3, 300, 15)), kn=6, same_libm=True)
 
 
 @pytest.mark.gpu
