@@ -71,11 +71,12 @@ __global__ void qg_codes_kernel (const uint8_t* __restrict__ tok, const uint64_t
 }
 
 // ---- the histogram kernel -------------------------------------------------------------------------
-// shared memory: cnt[ring] u32 | bkt[nk] u32 (start << 16 | length) | bpos[ymax] u16 | seedmask[STEP/32 + 2] u32
-// bpos holds, bucket by bucket, yLen - j for every k-mer start j of the read, so that a hit of reference position i
-// lands on ring slot (i + bpos) & (ring-1) = (d + yLen) & (ring-1) with one add and one and.
-// The full threshold scan of a finished window only runs if some counter of the block reached the threshold since the
-// last scan (the atomics return the old value); otherwise the window is just zeroed.
+// shared memory: cnt[ring] u32 | hdr[nk] uint2 | bpos[ymax] u16 | seedmask[STEP/32 + 2] u32
+//   hdr[code] = { first two bucket entries (16 bit each), start << 16 | length }   one LDS.64 per reference position
+//   bpos holds, bucket by bucket, span - j (span = yLen - k) for every k-mer start j of the read, so that a hit of
+//   reference position i lands on ring slot (i + bpos) & (ring-1) = (d + span) & (ring-1) with one add and one and.
+// A finished window of diagonals is read and cleared with 128-bit accesses; the seeds are only collected if some
+// counter of the block reached the threshold (block-wide OR), otherwise the window is just zeroed.
 template<bool COUNTS>
 __global__ void __launch_bounds__ (QG_SEED_THREADS)
 qg_seed_kernel (const qg_seed_item* __restrict__ items, const qg_pair_desc* __restrict__ pairs,
@@ -86,8 +87,8 @@ qg_seed_kernel (const qg_seed_item* __restrict__ items, const qg_pair_desc* __re
   QG_DYN_SMEM (smem);
   const uint32_t nk = 1u << (2 * k);
   uint32_t* cnt = (uint32_t*) smem;
-  uint32_t* bkt = cnt + ring;
-  uint16_t* bpos = (uint16_t*) (bkt + nk);
+  uint2* hdr = (uint2*) (cnt + ring);
+  uint16_t* bpos = (uint16_t*) (hdr + nk);
   uint32_t* seedmask = (uint32_t*) (bpos + ((ymax + 2) & ~1u));
   __shared__ uint32_t s_warp_tot[QG_SEED_THREADS / 32];
   __shared__ int s_open_lo, s_open_hi, s_have_open;
@@ -98,6 +99,7 @@ qg_seed_kernel (const qg_seed_item* __restrict__ items, const qg_pair_desc* __re
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int xlen = (int) pd.xlen, ylen = (int) pd.ylen;
   const int nyk = ylen - k + 1;                          // read k-mer starts j in [0, nyk)
+  const int span = ylen - k;                             // largest j
   const uint16_t* yc = ycodes + pd.yoff;
   const uint16_t* xc = xcodes + pd.xoff;
   const uint32_t mask = ring - 1;
@@ -108,12 +110,12 @@ qg_seed_kernel (const qg_seed_item* __restrict__ items, const qg_pair_desc* __re
   __syncthreads ();
   for (int j = tid; j < nyk; j += QG_SEED_THREADS) atomicAdd (&cnt[yc[j]], 1u);
   __syncthreads ();
+  const uint32_t per = (nk + QG_SEED_THREADS - 1) / QG_SEED_THREADS;
+  const uint32_t cb = tid * per, ce = (cb + per < nk) ? cb + per : nk;
   {
     // exclusive scan of cnt[0..nk) -> bucket starts; each thread owns a contiguous slice
-    const uint32_t per = (nk + QG_SEED_THREADS - 1) / QG_SEED_THREADS;
-    const uint32_t b = tid * per, e = (b + per < nk) ? b + per : nk;
     uint32_t sum = 0;
-    for (uint32_t c = b; c < e && c < nk; ++c) sum += cnt[c];
+    for (uint32_t c = cb; c < ce; ++c) sum += cnt[c];
     uint32_t incl = sum;
     for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync (QG_FULL_MASK, incl, o); if (lane >= o) incl += v; }
     if (lane == 31) s_warp_tot[wid] = incl;
@@ -121,23 +123,29 @@ qg_seed_kernel (const qg_seed_item* __restrict__ items, const qg_pair_desc* __re
     uint32_t wbase = 0;
     for (int w = 0; w < wid; ++w) wbase += s_warp_tot[w];
     uint32_t run = wbase + incl - sum;
-    for (uint32_t c = b; c < e && c < nk; ++c) { const uint32_t v = cnt[c]; bkt[c] = (run << 16) | v; cnt[c] = run; run += v; }
+    for (uint32_t c = cb; c < ce; ++c) { const uint32_t v = cnt[c]; hdr[c] = make_uint2 (0u, (run << 16) | v); cnt[c] = run; run += v; }
   }
   __syncthreads ();
-  for (int j = tid; j < nyk; j += QG_SEED_THREADS) { const uint32_t slot = atomicAdd (&cnt[yc[j]], 1u); bpos[slot] = (uint16_t) (ylen - j); }
+  for (int j = tid; j < nyk; j += QG_SEED_THREADS) { const uint32_t slot = atomicAdd (&cnt[yc[j]], 1u); bpos[slot] = (uint16_t) (span - j); }
   __syncthreads ();
+  for (uint32_t c = cb; c < ce; ++c) {                   // the first two entries of every bucket ride in its header
+    const uint32_t e = hdr[c].y, st = e >> 16, len = e & 0xFFFFu;
+    uint32_t x = 0;
+    if (len > 0) x = bpos[st];
+    if (len > 1) x |= (uint32_t) bpos[st + 1] << 16;
+    hdr[c].x = x;
+  }
   for (uint32_t c = tid; c < ring; c += QG_SEED_THREADS) cnt[c] = 0;
   __syncthreads ();
 
   // -- 2. slide along the reference
-  const int span = ylen - k;                              // largest j
   const int d_begin = it.d_begin, d_end = it.d_end;
   const int i_begin = d_begin > 0 ? d_begin : 0;
   int i_last = d_end - 1 + span;                          // inclusive
   if (i_last > xlen - k) i_last = xlen - k;
   const int min_diag = 1 - ylen, max_diag = xlen - 1;
   const uint32_t dlen = (uint32_t) (d_end - d_begin);
-  int emit_lo = d_begin;
+  int emit_lo = d_begin;                                  // (emit_lo + span) is always a multiple of 4
   uint32_t my_hits = 0;
   unsigned long long my_hits64 = 0;
 
@@ -150,55 +158,66 @@ qg_seed_kernel (const qg_seed_item* __restrict__ items, const qg_pair_desc* __re
     for (int r = 0; r < QG_SEED_PPT; ++r) {
       if (code[r] != 0xFFFFu) {
         const int i = i0 + r * QG_SEED_THREADS + tid;
-        const uint32_t e = bkt[code[r]];
-        const uint16_t* bp = bpos + (e >> 16);
-        const uint32_t len = e & 0xFFFFu;
+        const uint2 h = hdr[code[r]];
+        const uint32_t len = h.y & 0xFFFFu;
         if (i >= d_begin + span && i < d_end) {           // every diagonal this position can hit belongs to the item
-          // bucket lengths are Poisson(~2): the first four entries are predicated straight-line code (no loop
-          // bookkeeping, no divergence among lanes with different lengths), the rare longer tails loop
-          if (len > 0) atomicAdd (&cnt[(uint32_t) (i + (int) bp[0]) & mask], 1u);
-          if (len > 1) atomicAdd (&cnt[(uint32_t) (i + (int) bp[1]) & mask], 1u);
-          if (len > 2) atomicAdd (&cnt[(uint32_t) (i + (int) bp[2]) & mask], 1u);
-          if (len > 3) atomicAdd (&cnt[(uint32_t) (i + (int) bp[3]) & mask], 1u);
-          for (uint32_t t = 4; t < len; ++t) atomicAdd (&cnt[(uint32_t) (i + (int) bp[t]) & mask], 1u);
+          // bucket lengths are Poisson(~2): two entries come with the header, the next four are straight-line code,
+          // the rare longer tails loop
+          if (len > 0) atomicAdd (&cnt[((uint32_t) i + (h.x & 0xFFFFu)) & mask], 1u);
+          if (len > 1) atomicAdd (&cnt[((uint32_t) i + (h.x >> 16)) & mask], 1u);
+          if (len > 2) {
+            const uint16_t* bp = bpos + (h.y >> 16);
+            atomicAdd (&cnt[((uint32_t) i + bp[2]) & mask], 1u);
+            if (len > 3) atomicAdd (&cnt[((uint32_t) i + bp[3]) & mask], 1u);
+            if (len > 4) atomicAdd (&cnt[((uint32_t) i + bp[4]) & mask], 1u);
+            if (len > 5) atomicAdd (&cnt[((uint32_t) i + bp[5]) & mask], 1u);
+            for (uint32_t t = 6; t < len; ++t) atomicAdd (&cnt[((uint32_t) i + bp[t]) & mask], 1u);
+          }
           my_hits += len;
         } else {
-          const uint32_t ib = (uint32_t) (i - ylen - d_begin);     // d - d_begin = ib + bp[t]
+          const uint16_t* bp = bpos + (h.y >> 16);
+          const uint32_t ib = (uint32_t) (i - span - d_begin);     // d - d_begin = ib + bp[t]
           for (uint32_t t = 0; t < len; ++t) {
             const uint32_t v = bp[t];
-            if (ib + v < dlen) { atomicAdd (&cnt[(uint32_t) (i + (int) v) & mask], 1u); ++my_hits; }
+            if (ib + v < dlen) { atomicAdd (&cnt[((uint32_t) i + v) & mask], 1u); ++my_hits; }
           }
         }
       }
     }
     if (my_hits > 0x40000000u) { my_hits64 += my_hits; my_hits = 0; }
     __syncthreads ();
-    // diagonals below i1 - span can receive no further hits
-    int emit_hi = (i1 > i_last) ? d_end : i1 - span;
+    // diagonals below i1 - span can receive no further hits; windows end on a 4-slot boundary except the last one
+    int emit_hi = (i1 > i_last) ? d_end : (i1 - span) - (i1 & 3);
     if (emit_hi > d_end) emit_hi = d_end;
     if (emit_hi > emit_lo) {
-      // finished diagonals: every thread reads and clears its share (lanes of a warp hold 32 consecutive diagonals); only
-      // if some counter of the block reached the threshold are the seeds collected, in ascending order, by thread 0
       for (int base = emit_lo; base < emit_hi; base += QG_SEED_STEP) {
-        uint32_t c[QG_SEED_PPT];
+        uint32_t nib[QG_SEED_PPT / 4];
         bool hot = false;
 #pragma unroll
-        for (int r = 0; r < QG_SEED_PPT; ++r) {
-          const int d = base + r * QG_SEED_THREADS + tid;
-          c[r] = 0;
-          if (d < emit_hi) {
-            const uint32_t idx = (uint32_t) (d + ylen) & mask;
-            c[r] = cnt[idx]; cnt[idx] = 0;
-            if (COUNTS) { counts_out[pd.count_off + (uint64_t) (d + span)] = c[r]; c[r] = 0; }     // memory-guided mode: raw counts only
+        for (int q = 0; q < QG_SEED_PPT / 4; ++q) {
+          const int d0 = base + (q * QG_SEED_THREADS + tid) * 4;
+          nib[q] = 0;
+          if (d0 < emit_hi) {
+            uint4* p4 = (uint4*) (cnt + ((uint32_t) (d0 + span) & mask));
+            const uint4 c = *p4;
+            *p4 = make_uint4 (0u, 0u, 0u, 0u);
+            const uint32_t cc[4] = { c.x, c.y, c.z, c.w };
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              if (d0 + e < emit_hi) {
+                if (COUNTS) counts_out[pd.count_off + (uint64_t) (d0 + e + span)] = cc[e];     // memory-guided mode: raw counts only
+                else if ((int) cc[e] >= threshold && cc[e] > 0) nib[q] |= 1u << e;
+              }
+            }
           }
-          hot = hot || ((int) c[r] >= threshold && c[r] > 0);
+          hot = hot || nib[q] != 0;
         }
         if (__syncthreads_or (hot ? 1 : 0)) {
+          for (int w = tid; w < QG_SEED_STEP / 32; w += QG_SEED_THREADS) seedmask[w] = 0;
+          __syncthreads ();
 #pragma unroll
-          for (int r = 0; r < QG_SEED_PPT; ++r) {
-            const uint32_t m = __ballot_sync (QG_FULL_MASK, (int) c[r] >= threshold && c[r] > 0);
-            if (lane == 0) seedmask[r * (QG_SEED_THREADS / 32) + wid] = m;
-          }
+          for (int q = 0; q < QG_SEED_PPT / 4; ++q)
+            if (nib[q]) { const uint32_t bit = (uint32_t) (q * QG_SEED_THREADS + tid) * 4; atomicOr (&seedmask[bit >> 5], nib[q] << (bit & 31)); }
           __syncthreads ();
           if (tid == 0) {
             // seeds in ascending order -> union of [seed-half, seed+half] clipped to the matrix (diagenv.cpp:79-84)

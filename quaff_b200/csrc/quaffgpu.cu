@@ -299,10 +299,10 @@ struct qg_env_result {
 // or the general path (sorted read index + per-diagonal counters in HBM)
 static size_t qg_seed_smem_bytes (int k, uint32_t ymax, uint32_t* ring_out) {
   const uint32_t nk = 1u << (2 * k);
-  uint32_t need = std::max<uint32_t> (nk, QG_SEED_STEP + ymax + 1), ring = 1;
+  uint32_t need = std::max<uint32_t> (nk, QG_SEED_STEP + ymax + 4), ring = 1;
   while (ring < need) ring <<= 1;
   if (ring_out) *ring_out = ring;
-  return (size_t) ring * 4 + (size_t) nk * 4 + (size_t) ((ymax + 2) & ~1u) * 2 + (QG_SEED_STEP / 32 + 2) * 4;
+  return (size_t) ring * 4 + (size_t) nk * 8 + (size_t) ((ymax + 2) & ~1u) * 2 + (QG_SEED_STEP / 32 + 2) * 4;
 }
 static bool qg_pair_is_sparse (const qg_dpconfig* cfg, uint32_t xlen, uint32_t ylen) {
   if (!cfg->sparse) return false;
