@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libquaffgpu.so")
 SOURCES = ["quaffgpu.cu"]
-HEADERS = ["qg_common.cuh", "qg_seed.cuh", "qg_dp.cuh", "qg_backward.cuh", "qg_overlap.cuh", "qg_host.cuh", os.path.join("..", "..", "include", "quaffgpu.h")]
+HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith(".cuh")) + [os.path.join("..", "..", "include", "quaffgpu.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

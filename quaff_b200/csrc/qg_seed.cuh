@@ -14,7 +14,12 @@
 #define QG_SEED_CUH
 #include "qg_common.cuh"
 
-#define QG_SEED_THREADS 512
+#ifndef QG_SEED_THREADS
+#define QG_SEED_THREADS 768
+#endif
+#ifndef QG_SEED_MINB
+#define QG_SEED_MINB 2             /* two CTAs per SM: caps registers at 40 */
+#endif
 #define QG_SEED_PPT 8                // reference positions per thread per step
 #define QG_SEED_STEP (QG_SEED_THREADS * QG_SEED_PPT)   // reference positions consumed between two emit scans
 #define QG_SEED_CHUNK (192 * 1024)   // diagonals owned by one work item
@@ -78,7 +83,7 @@ __global__ void qg_codes_kernel (const uint8_t* __restrict__ tok, const uint64_t
 // A finished window of diagonals is read and cleared with 128-bit accesses; the seeds are only collected if some
 // counter of the block reached the threshold (block-wide OR), otherwise the window is just zeroed.
 template<bool COUNTS>
-__global__ void __launch_bounds__ (QG_SEED_THREADS)
+__global__ void __launch_bounds__ (QG_SEED_THREADS, QG_SEED_MINB)
 qg_seed_kernel (const qg_seed_item* __restrict__ items, const qg_pair_desc* __restrict__ pairs,
                 const uint16_t* __restrict__ xcodes, const uint16_t* __restrict__ ycodes,
                 int k, int threshold, int half_band, uint32_t ring, uint32_t ymax, uint32_t run_cap,

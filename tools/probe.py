@@ -21,6 +21,7 @@ ap.add_argument("--read-len", type=int, default=8000)
 ap.add_argument("--forward", action="store_true")
 ap.add_argument("--backward", action="store_true")
 ap.add_argument("--reps", type=int, default=2)
+ap.add_argument("--lib", default=None)
 a = ap.parse_args()
 
 t0 = time.time()
@@ -29,7 +30,7 @@ reads, _, _ = sample_reads(ref, a.reads, a.read_len, 2)
 x = add_revcomps([ref])
 print(f"synth {time.time() - t0:.1f}s", flush=True)
 qp = QuaffParams.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "defaultparams.json"))
-G = api.QuaffGPU()
+G = api.QuaffGPU(lib_path=a.lib) if a.lib else api.QuaffGPU()
 G.set_refs(x); G.set_reads(reads); G.set_params(qp)
 cfg = api.dp_config(kmer_threshold=20)
 xi = np.tile(np.arange(2, dtype=np.uint32), len(reads)); yi = np.repeat(np.arange(len(reads), dtype=np.uint32), 2)
