@@ -94,7 +94,7 @@ struct qg_rp_job { uint32_t yseq, ylen; uint64_t yoff, rp_off; };
 
 __global__ void qg_rowparams_kernel (const qg_rp_job* __restrict__ jobs, const uint8_t* __restrict__ ytok, const uint8_t* __restrict__ yqual,
                                      const double* __restrict__ match, const double* __restrict__ insert, const double* __restrict__ gap,
-                                     int match_k, int gap_k, qg_rowp* __restrict__ rp) {
+                                     int match_k, int gap_k, qg_rowp* __restrict__ rp, double2* __restrict__ rps) {
   __shared__ unsigned s_count[4];
   __shared__ int s_mf;
   const qg_rp_job jb = jobs[blockIdx.x];
@@ -134,6 +134,12 @@ __global__ void qg_rowparams_kernel (const qg_rp_job* __restrict__ jobs, const u
       }
     }
     out[j] = r;
+    if (rps) {                                              // structure-of-arrays copy for qg_vit_kernel
+      double2* o2 = rps + 4 * jb.rp_off + j;
+      const uint64_t rows = (uint64_t) ylen + 2;
+      o2[0] = make_double2 (r.e[0], r.e[1]); o2[rows] = make_double2 (r.e[2], r.e[3]);
+      o2[2 * rows] = make_double2 (r.ins, r.m2m); o2[3 * rows] = make_double2 (r.m2i, r.m2d);
+    }
   }
 }
 

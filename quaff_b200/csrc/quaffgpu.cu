@@ -8,6 +8,7 @@
 #include "qg_overlap.cuh"
 #include "qg_prob.cuh"
 #include "qg_tile.cuh"
+#include "qg_vit.cuh"
 #ifndef QG_EMU
 #include <cub/device/device_segmented_radix_sort.cuh>
 #endif
@@ -20,7 +21,7 @@ enum {
   SC_PAIRDESC = 0, SC_ITEMS, SC_ITEMRUNS, SC_ITEMNRUNS, SC_PAIRRUNS, SC_PAIRINFO, SC_PAIRCU, SC_FLAGS,
   SC_SEGS, SC_RPJOBS, SC_RP, SC_TRACE, SC_ENDVALS, SC_PAIRDP, SC_OUT0, SC_OUT1, SC_OUT2, SC_OUT3, SC_PATHSCR, SC_PATHOUT,
   SC_STORE, SC_ROWACC, SC_MISC0, SC_MISC1, SC_RQ, SC_RS, SC_ENDEX, SC_STOREEX, SC_ZM, SC_ZE,
-  SC_XC64, SC_YC64, SC_KEYS0, SC_KEYS1, SC_VALS0, SC_VALS1, SC_IDXJOBS, SC_SEGOFF, SC_SORTTMP
+  SC_RPS, SC_XC64, SC_YC64, SC_KEYS0, SC_KEYS1, SC_VALS0, SC_VALS1, SC_IDXJOBS, SC_SEGOFF, SC_SORTTMP
 };
 
 // ---- small helpers -----------------------------------------------------------------------------------
@@ -706,6 +707,10 @@ static int qg_launch_fill (qg_ctx* ctx, const qg_dp_plan& plan, qg_fill_args a, 
     const unsigned block = 32u * L.nw;
 #define QG_CASE(RR) case RR: \
       if (multi) { auto kfn = qg_fill_kernel<8, MODE, true>; QG_LAUNCH (kfn, L.count, block, 0, st, a); } \
+      else if (MODE == 0 && !getenv ("QG_VIT_GENERIC")) { \
+        qg_vit_args va; va.segs = a.segs; va.xpacked = a.xpacked; va.xpoff = a.xpoff; va.rps = ctx->scratch[SC_RPS].as<double2> (); \
+        va.i2i = a.i2i; va.i2m = a.i2m; va.d2d = a.d2d; va.d2m = a.d2m; va.local = a.local; va.trace = a.trace; va.endvals = a.endvals; \
+        auto kfn = qg_vit_kernel<RR>; QG_LAUNCH (kfn, L.count, block, 0, st, va); } \
       else { auto kfn = qg_fill_kernel<RR, MODE, false>; QG_LAUNCH (kfn, L.count, block, 0, st, a); } break;
     switch (L.R) {
       QG_CASE (2) QG_CASE (3) QG_CASE (4) QG_CASE (5) QG_CASE (6) QG_CASE (7) QG_CASE (8)
@@ -723,10 +728,12 @@ static int qg_stage_rowparams (qg_ctx* ctx, const qg_dp_plan& plan) {
   const qg_model_dev& m = ctx->model;
   QG_TRY (qg_upload (ctx, ctx->scratch[SC_RPJOBS], plan.rp_jobs.data (), sizeof (qg_rp_job) * plan.rp_jobs.size ()));
   QG_TRY (qg_reserve (ctx, ctx->scratch[SC_RP], sizeof (qg_rowp) * (plan.rp_rows + 1)));
+  QG_TRY (qg_reserve (ctx, ctx->scratch[SC_RPS], sizeof (qg_rowp) * (plan.rp_rows + 1)));
   if (!plan.rp_jobs.empty ()) {
     QG_LAUNCH (qg_rowparams_kernel, (unsigned) plan.rp_jobs.size (), 256, 0, ctx->stream,
                ctx->scratch[SC_RPJOBS].as<qg_rp_job> (), Y.d_tok.as<uint8_t> (), Y.has_qual ? Y.d_qual.as<uint8_t> () : (const uint8_t*) nullptr,
-               m.d_match.as<double> (), m.d_insert.as<double> (), m.d_gap.as<double> (), m.match_k, m.gap_k, ctx->scratch[SC_RP].as<qg_rowp> ());
+               m.d_match.as<double> (), m.d_insert.as<double> (), m.d_gap.as<double> (), m.match_k, m.gap_k, ctx->scratch[SC_RP].as<qg_rowp> (),
+               ctx->scratch[SC_RPS].as<double2> ());
     QG_TRY (qg_check_launch (ctx, "qg_rowparams_kernel"));
   }
   return QG_OK;
