@@ -417,7 +417,8 @@ qg_traceback_warp_kernel (const qg_pair_dp* __restrict__ pairs, uint32_t npairs,
     int u_top = 0;
     if (lane == 0 && state != 0 && !fail) u_top = j + (i - j - sg.dlo) / R;
     u_top = __shfl_sync (QG_FULL_MASK, u_top, 0);
-    const bool multi = sg.nwarps > 1;
+    const bool multi = sg.nwarps != 1;                      // more than one warp, or a narrow segment (nwarps == 0): direct loads
+    const bool narrow = sg.nwarps == 0;                     // one u32 per row, nibble = slot (qg_vit_narrow_kernel)
     if (!multi) {
 #pragma unroll 8
       for (int r = 0; r < 32; ++r) {
@@ -434,7 +435,8 @@ qg_traceback_warp_kernel (const qg_pair_dp* __restrict__ pairs, uint32_t npairs,
         const int vl = slot / R, c = slot - vl * R;
         const int u = j + vl;
         uint32_t word;
-        if (multi) word = trace[sg.trace_off + (uint64_t) u * (32 * sg.nwarps) + vl];
+        if (narrow) word = trace[sg.trace_off + (uint64_t) j] >> (4 * (slot - c));
+        else if (multi) word = trace[sg.trace_off + (uint64_t) u * (32 * sg.nwarps) + vl];
         else {
           if (u < u_top - 31) break;                                       // next tile
           word = s_tile[w][u_top - u][vl];

@@ -159,4 +159,81 @@ qg_vit_kernel (const qg_vit_args a) {
   if (L.vl == 0) { a.endvals[2 * sg.aux_off] = bestEnd; a.endvals[2 * sg.aux_off + 1] = (double) bestI; }
 }
 
+
+// ---- narrow segments: runs of 1..4 diagonals (the always-present diagonal 0 of every pair, diagenv.cpp:52-54) ----
+// A warp per run would spend yLen + 31 macro-steps on a handful of cells per row.  Here one THREAD fills one run, row by
+// row, cells in ascending i (so Delete sees this row's left neighbour and Insert the previous row's right neighbour);
+// same expressions and pointer rules.  Pointer layout of these segments (nwarps == 0): one u32 per row j at
+// trace_off + j, nibble c = slot; four rows are written as one 16 B store.
+template<int W>
+__global__ void __launch_bounds__ (64)
+qg_vit_narrow_kernel (const qg_vit_args a, uint32_t nseg) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nseg) return;
+  const qg_segment sg = a.segs[t];
+  const int xlen = (int) sg.xlen, ylen = (int) sg.ylen, dlo = sg.dlo;
+  const uint64_t* xw = a.xpacked + a.xpoff[sg.xseq];
+  const int nxw = (xlen + 31) >> 5;
+  const int rows = ylen + 2;
+  const double2* rq = a.rps + 4 * sg.rp_off;
+  const double i2i = a.i2i, i2m = a.i2m, d2d = a.d2d, d2m = a.d2m;
+  const bool local = a.local != 0;
+  const double m2e = rq[2 * rows].y;
+  double M[W], I[W], D[W];
+#pragma unroll
+  for (int c = 0; c < W; ++c) { M[c] = QG_NEG_INF; I[c] = QG_NEG_INF; D[c] = QG_NEG_INF; }
+  double bestEnd = QG_NEG_INF; int bestI = 0;
+  uint64_t win = 0; int pw = 0; bool have_win = false;
+  uint32_t* tr = a.trace + sg.trace_off;
+  uint32_t acc[4] = {0u, 0u, 0u, 0u};
+  double2 Pn[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) Pn[q] = rq[q * rows + 1];
+  for (int j = 1; j <= ylen; ++j) {
+    const double2 q0 = Pn[0], q1 = Pn[1], q2 = Pn[2], q3 = Pn[3];
+    const double e[4] = { q0.x, q0.y, q1.x, q1.y };
+    const double ins = q2.x, m2m = q2.y, m2i = q3.x, m2d = q3.y;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) Pn[q] = rq[q * rows + j + 1];               // row yLen+1 exists (zero filler)
+    const int p0 = dlo + j - 1;
+    if (!have_win || p0 < pw || p0 + W > pw + 32) { win = qg_fetch32 (xw, nxw, p0); pw = p0; have_win = true; }
+    const uint64_t wsh = win >> (2 * ((p0 - pw) & 31));
+    const bool startRow = (j == 1), endRow = (j == ylen);
+    unsigned tword = 0;
+    double leftM = QG_NEG_INF, leftD = QG_NEG_INF;                          // halo diagonal dlo - 1
+#pragma unroll
+    for (int c = 0; c < W; ++c) {
+      const int i = dlo + c + j;
+      const bool ok = (i >= 1) && (i <= xlen);
+      const double E = qg_sel4 (e, (int) ((wsh >> (2 * c)) & 3));
+      const double mM = M[c], mI = I[c], mD = D[c];
+      const double iM = (c + 1 < W) ? M[(c + 1) % W] : QG_NEG_INF;          // halo diagonal dlo + W
+      const double iI = (c + 1 < W) ? I[(c + 1) % W] : QG_NEG_INF;
+      unsigned ptr = 0;
+      const double cM = (mM + m2m) + E, cI = (mI + i2m) + E, cD = (mD + d2m) + E;
+      double nM = cM;
+      if (cI > nM) { nM = cI; ptr = 1; }
+      if (cD > nM) { nM = cD; ptr = 2; }
+      if (startRow && (i == 1 || local) && E > nM) { nM = E; ptr = 3; }
+      const double aM = (iM + m2i) + ins, aI = (iI + i2i) + ins;
+      double nI = aM;
+      if (aI > nI) { nI = aI; ptr |= 4; }
+      const double bM = leftM + m2d, bD = leftD + d2d;
+      double nD = bM;
+      if (bD > nD) { nD = bD; ptr |= 8; }
+      if (!ok) { nM = QG_NEG_INF; nI = QG_NEG_INF; nD = QG_NEG_INF; ptr = 0; }
+      M[c] = nM; I[c] = nI; D[c] = nD;
+      leftM = nM; leftD = nD;
+      tword |= ptr << (4 * c);
+      if (endRow) {
+        const bool isEnd = ok && (i == xlen || local);
+        if (isEnd) { const double en = nM + m2e; if (en >= bestEnd) { bestEnd = en; bestI = i; } }
+      }
+    }
+    acc[j & 3] = tword;
+    if ((j & 3) == 3 || j == ylen) *(uint4*) (tr + (j & ~3)) = make_uint4 (acc[0], acc[1], acc[2], acc[3]);
+  }
+  a.endvals[2 * sg.aux_off] = bestEnd; a.endvals[2 * sg.aux_off + 1] = (double) bestI;
+}
+
 #endif

@@ -669,7 +669,9 @@ static int qg_build_plan (qg_ctx* ctx, const qg_env_result& er, size_t p0, size_
       sg.R = (uint32_t) R; sg.nwarps = (uint32_t) nw;
       sg.rp_off = it->second;
       const uint64_t lanes = 32ull * nw;
-      if (mode == 0 || mode == 3) { sg.trace_off = plan.trace_words; plan.trace_words += ((uint64_t) pp.ylen + lanes + 1) * lanes; }
+      const bool narrow = mode == 0 && sg.width <= 4 && !getenv ("QG_VIT_GENERIC");    // one thread per run (qg_vit_narrow_kernel)
+      if (narrow) { sg.R = sg.width; sg.nwarps = 0; sg.trace_off = plan.trace_words; plan.trace_words += (((uint64_t) pp.ylen + 4) / 4) * 4; }
+      else if (mode == 0 || mode == 3) { sg.trace_off = plan.trace_words; plan.trace_words += ((uint64_t) pp.ylen + lanes + 1) * lanes; }
       if (mode == 3) { sg.acc_off = plan.acc_rows; plan.acc_rows += (uint64_t) pp.ylen + 2; }
       if (mode == 2) { sg.store_off = plan.store_doubles; plan.store_doubles += ((uint64_t) pp.ylen + lanes + 1) * 3 * lanes * R;
                        sg.acc_off = plan.acc_rows; plan.acc_rows += (uint64_t) pp.ylen + 2; }
@@ -703,6 +705,20 @@ static int qg_launch_fill (qg_ctx* ctx, const qg_dp_plan& plan, qg_fill_args a, 
   for (const auto& L : plan.launches) {
     cudaStream_t st; QG_TRY (qg_side (ctx, kcls++, &st));
     a.segs = d_segs_launch_order + L.begin;
+    if (L.nw == 0) {                                        // narrow Viterbi segments, one thread each
+      qg_vit_args va; va.segs = a.segs; va.xpacked = a.xpacked; va.xpoff = a.xpoff; va.rps = ctx->scratch[SC_RPS].as<double2> ();
+      va.i2i = a.i2i; va.i2m = a.i2m; va.d2d = a.d2d; va.d2m = a.d2m; va.local = a.local; va.trace = a.trace; va.endvals = a.endvals;
+      const unsigned grid = (L.count + 63) / 64;
+      switch (L.R) {
+        case 1: QG_LAUNCH (qg_vit_narrow_kernel<1>, grid, 64, 0, st, va, L.count); break;
+        case 2: QG_LAUNCH (qg_vit_narrow_kernel<2>, grid, 64, 0, st, va, L.count); break;
+        case 3: QG_LAUNCH (qg_vit_narrow_kernel<3>, grid, 64, 0, st, va, L.count); break;
+        case 4: QG_LAUNCH (qg_vit_narrow_kernel<4>, grid, 64, 0, st, va, L.count); break;
+        default: QG_FAIL (ctx, QG_ERR_INVALID, "internal: narrow segment of width %d", L.R);
+      }
+      QG_TRY (qg_check_launch (ctx, "qg_vit_narrow_kernel"));
+      continue;
+    }
     const bool multi = L.nw > 1;
     const unsigned block = 32u * L.nw;
 #define QG_CASE(RR) case RR: \
