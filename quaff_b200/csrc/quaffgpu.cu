@@ -490,8 +490,10 @@ static int qg_envelope_stage_cap (qg_ctx* ctx, const qg_dpconfig* cfg, uint64_t 
     const size_t smem = qg_seed_smem_bytes (k, ymax, &ring);
     if (smem > ctx->smem_optin)
       QG_FAIL (ctx, QG_ERR_CUDA, "internal: seeding kernel selection (%zu B of shared memory needed, limit %zu)", smem, ctx->smem_optin);
-    QG_CUDA (ctx, cudaFuncSetAttribute (qg_seed_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-    QG_CUDA (ctx, cudaFuncSetAttribute (qg_seed_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    // the attribute belongs to the function, not to this context: always the device maximum, so that contexts running
+    // on other host threads with other read lengths never shrink it under a launch
+    QG_CUDA (ctx, cudaFuncSetAttribute (qg_seed_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ctx->smem_optin));
+    QG_CUDA (ctx, cudaFuncSetAttribute (qg_seed_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ctx->smem_optin));
     {
       qg_timer tm (ctx, &ctx->stats.ms_seed);
       auto kfn = memory_mode ? qg_seed_kernel<true> : qg_seed_kernel<false>;
