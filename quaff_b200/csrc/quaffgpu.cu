@@ -115,7 +115,7 @@ extern "C" int qg_create (qg_ctx** out, int device) {
   cudaDeviceProp prop;
   if ((e = cudaGetDeviceProperties (&prop, device)) != cudaSuccess) return fail ("cudaGetDeviceProperties", e);
   ctx->sm_count = prop.multiProcessorCount;
-  ctx->smem_optin = prop.sharedMemPerBlockOptin;
+  ctx->smem_optin = prop.sharedMemPerBlockOptin > 2048 ? prop.sharedMemPerBlockOptin - 1024 : prop.sharedMemPerBlockOptin;   // dynamic budget: leave room for the kernels' static shared memory
   if ((e = cudaStreamCreateWithFlags (&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail ("cudaStreamCreate", e);
   if ((e = cudaEventCreate (&ctx->ev[0])) != cudaSuccess) return fail ("cudaEventCreate", e);
   if ((e = cudaEventCreate (&ctx->ev[1])) != cudaSuccess) return fail ("cudaEventCreate", e);

@@ -158,9 +158,9 @@ def test_probability_space_order2_and_global(gpu, oracle):
 
 
 def test_wide_runs_tiled(gpu, oracle):
-    """-kmatchoff on 20 kb references: one run of > 8192 diagonals per pair goes through the i-space tile
+    """-kmatchoff on a 9 kb reference: one run of > 8192 diagonals per pair goes through the i-space tile
     wavefront (qg_tile.cuh); Viterbi score / interval / path and Forward stay bit-exact"""
-    x, reads = pc.make_workload(ref_len=20000, n_reads=3, read_len=2000, seed=23, n_refs=2)
+    x, reads = pc.make_workload(ref_len=9000, n_reads=2, read_len=1500, seed=23)
     qp = pc.default_params()
     gpu.set_refs(x); gpu.set_reads(reads); gpu.set_params(qp)
     s_or = oracle.scores(qp)
