@@ -230,7 +230,7 @@ __global__ void qg_forward_prob_finalize_kernel (const qg_pair_dp* __restrict__ 
 
 // ---- Backward + counts, probability space, pull form (see qg_backward.cuh for the structure) -------------------------
 template<int R>
-__global__ void __launch_bounds__ (32, 14)
+__global__ void __launch_bounds__ (32, 12)
 qg_backward_prob_kernel (const qg_prob_args a) {
   const qg_segment sg = a.segs[blockIdx.x];
   const int lane = threadIdx.x;
@@ -265,7 +265,29 @@ qg_backward_prob_kernel (const qg_prob_args a) {
   qg_rowq Pn = rq[ylen + 1];
 
   const int total = ylen + 31;
+  // the stored Forward record of a macro-step (3R mantissas + exponent, written by the Forward lane that owns my slots at
+  // its macro-step yLen + 32 - u) is fetched one macro-step ahead: a warp is one long dependent chain and there are
+  // few warps per SM, so an HBM round trip per step would otherwise be fully exposed
+  double pf[3 * R]; int pfex;
+  {
+    const uint64_t fr = (uint64_t) (ylen + 32 - 1) * 32 + flane;
+    const double* s1 = stbase + fr * (3 * R);
+#pragma unroll
+    for (int t = 0; t < 3 * R; ++t) pf[t] = s1[t];
+    pfex = stex[fr];
+  }
   for (int u = 1; u <= total; ++u) {
+    double st[3 * R];
+#pragma unroll
+    for (int t = 0; t < 3 * R; ++t) st[t] = pf[t];
+    const int stex_cur = pfex;
+    if (u < total) {
+      const uint64_t fr = (uint64_t) (ylen + 32 - (u + 1)) * 32 + flane;
+      const double* s1 = stbase + fr * (3 * R);
+#pragma unroll
+      for (int t = 0; t < 3 * R; ++t) pf[t] = s1[t];
+      pfex = stex[fr];
+    }
     const int j = ylen + 1 - (u - lane);
     const bool active = (j >= 1) && (j <= ylen);
     const int jj = j < 0 ? 0 : (j > ylen + 1 ? ylen + 1 : j);
@@ -283,9 +305,7 @@ qg_backward_prob_kernel (const qg_prob_args a) {
       rec = in;
     }
     // the Forward warp wrote this row's cells of my slots at its macro-step j + flane = yLen + 32 - u: one block per step
-    const uint64_t frec = (uint64_t) (ylen + 32 - u) * 32 + flane;
-    const double* st = stbase + frec * (3 * R);
-    const int exF = (active && zok) ? stex[frec] : 0;
+    const int exF = (active && zok) ? stex_cur : 0;
     double K = rzm * qg_pow2 (exF + ex - ze);               // count = f * candidate * K (true scale)
     double rI = 0;
     double mx = 0;
