@@ -328,17 +328,17 @@ def main():
         # DRAM traffic of the dominant kernel per launch, from the committed ncu --set full capture of this same workload
         traffic = None
         try:
-            tj = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01c_traffic.json")))
+            tj = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01g_traffic.json")))
             w = tj["workload"]
             if (w["reads_per_launch"], w["ref_len"], w["read_len"]) == (iso_reads // n_iso, args.ref_len, args.read_len):
-                k = tj["qg_seed_kernel" if seed_dom else "qg_fill_kernel<3,0,0>"]
+                k = tj["qg_seed_kernel" if seed_dom else "qg_vit_kernel<3>"]
                 traffic = k["dram_bytes_read"] + k["dram_bytes_write"]
         except Exception:
             traffic = None
         seed_gbps = seed_bytes / (ms_seed / 1e3) / 1e9
         vit_gbps = vit_bytes / (ms_vit / 1e3) / 1e9
         compute = {
-            "kernel": "qg_seed_kernel" if seed_dom else "qg_fill_kernel<R,Viterbi>",
+            "kernel": "qg_seed_kernel" if seed_dom else "qg_vit_kernel<R>",
             "bound": "smem_atomic" if seed_dom else "fp64_issue",
             "achieved": seed_hps / 1e9 if seed_dom else vit_cups / 1e9,
             "peak": PEAK_SMEM_ATOMIC / 1e9 if seed_dom else PEAK_LANE_INSTR / INSTR_PER_CU["viterbi"] / 1e9,

@@ -186,15 +186,27 @@ qg_vit_narrow_kernel (const qg_vit_args a, uint32_t nseg) {
   uint64_t win = 0; int pw = 0; bool have_win = false;
   uint32_t* tr = a.trace + sg.trace_off;
   uint32_t acc[4] = {0u, 0u, 0u, 0u};
-  double2 Pn[4];
+  // a single thread is one long dependent chain and there are few of them: row parameters are fetched four rows ahead
+  double2 ring[4][4];
 #pragma unroll
-  for (int q = 0; q < 4; ++q) Pn[q] = rq[q * rows + 1];
-  for (int j = 1; j <= ylen; ++j) {
-    const double2 q0 = Pn[0], q1 = Pn[1], q2 = Pn[2], q3 = Pn[3];
+  for (int k = 0; k < 4; ++k) {
+    const int jr = (1 + k > ylen + 1) ? ylen + 1 : 1 + k;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) ring[k][q] = rq[q * rows + jr];
+  }
+  for (int j0 = 1; j0 <= ylen; j0 += 4) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int j = j0 + k;
+    if (j > ylen) break;
+    const double2 q0 = ring[k][0], q1 = ring[k][1], q2 = ring[k][2], q3 = ring[k][3];
     const double e[4] = { q0.x, q0.y, q1.x, q1.y };
     const double ins = q2.x, m2m = q2.y, m2i = q3.x, m2d = q3.y;
+    {
+      const int jr = (j + 4 > ylen + 1) ? ylen + 1 : j + 4;                 // row yLen+1 exists (zero filler)
 #pragma unroll
-    for (int q = 0; q < 4; ++q) Pn[q] = rq[q * rows + j + 1];               // row yLen+1 exists (zero filler)
+      for (int q = 0; q < 4; ++q) ring[k][q] = rq[q * rows + jr];
+    }
     const int p0 = dlo + j - 1;
     if (!have_win || p0 < pw || p0 + W > pw + 32) { win = qg_fetch32 (xw, nxw, p0); pw = p0; have_win = true; }
     const uint64_t wsh = win >> (2 * ((p0 - pw) & 31));
@@ -232,6 +244,7 @@ qg_vit_narrow_kernel (const qg_vit_args a, uint32_t nseg) {
     }
     acc[j & 3] = tword;
     if ((j & 3) == 3 || j == ylen) *(uint4*) (tr + (j & ~3)) = make_uint4 (acc[0], acc[1], acc[2], acc[3]);
+  }
   }
   a.endvals[2 * sg.aux_off] = bestEnd; a.endvals[2 * sg.aux_off + 1] = (double) bestI;
 }
