@@ -138,6 +138,7 @@ extern "C" int qg_create (qg_ctx** out, int device) {
 }
 
 extern "C" void qg_destroy (qg_ctx* ctx) {
+  if (ctx) cudaSetDevice (ctx->device);                    // the caller may be a host thread that never selected this context's GPU
   if (!ctx) return;
   cudaSetDevice (ctx->device);
   cudaStreamSynchronize (ctx->stream);
@@ -171,6 +172,7 @@ extern "C" int qg_get_stats (qg_ctx* ctx, qg_stats* out, int reset) {
 
 // ---- inputs ----------------------------------------------------------------------------------------------
 extern "C" int qg_set_seqs (qg_ctx* ctx, int which, size_t n, const uint8_t* tok, const uint8_t* qual, const uint64_t* offsets) {
+  if (ctx) cudaSetDevice (ctx->device);                    // the caller may be a host thread that never selected this context's GPU
   if (!ctx) return QG_ERR_INVALID;
   if (which != QG_REFS && which != QG_READS) QG_FAIL (ctx, QG_ERR_INVALID, "qg_set_seqs: unknown sequence set %d", which);
   if (!offsets || (n && !tok)) QG_FAIL (ctx, QG_ERR_INVALID, "qg_set_seqs: null pointer");
@@ -232,6 +234,7 @@ static int qg_ensure_codes (qg_ctx* ctx, int which, int k) {
 }
 
 extern "C" int qg_set_align_model (qg_ctx* ctx, const qg_align_model* m) {
+  if (ctx) cudaSetDevice (ctx->device);                    // the caller may be a host thread that never selected this context's GPU
   if (!ctx || !m) return QG_ERR_INVALID;
   if (m->match_k < 1 || m->match_k > 6 || m->gap_k < 0 || m->gap_k > 6) QG_FAIL (ctx, QG_ERR_UNSUPPORTED, "model orders K=%d G=%d outside 1..6 / 0..6", m->match_k, m->gap_k);
   qg_model_dev& d = ctx->model;
@@ -604,6 +607,7 @@ static int qg_envelope_stage (qg_ctx* ctx, const qg_dpconfig* cfg, uint64_t cell
 extern "C" int qg_envelopes (qg_ctx* ctx, const qg_dpconfig* cfg, uint64_t cell_size, int x_set,
                              size_t n_pairs, const uint32_t* xi, const uint32_t* yi,
                              int32_t** diags_out, uint64_t* diag_offsets, uint64_t* cell_updates) {
+  if (ctx) cudaSetDevice (ctx->device);                    // the caller may be a host thread that never selected this context's GPU
   if (!ctx || !cfg || !xi || !yi || !diags_out || !diag_offsets) return QG_ERR_INVALID;
   if (x_set != QG_REFS && x_set != QG_READS) QG_FAIL (ctx, QG_ERR_INVALID, "x_set must be QG_REFS or QG_READS");
   qg_env_result er;
@@ -1170,6 +1174,7 @@ static int qg_viterbi_impl (qg_ctx* ctx, const qg_dpconfig* cfg, size_t n_pairs,
 extern "C" int qg_viterbi (qg_ctx* ctx, const qg_dpconfig* cfg, size_t n_pairs, const uint32_t* xi, const uint32_t* yi,
                            const uint8_t* want_path, double* score, uint32_t* x_start, uint32_t* x_end,
                            uint8_t** path_out, uint64_t* path_offsets) {
+  if (ctx) cudaSetDevice (ctx->device);                    // the caller may be a host thread that never selected this context's GPU
   if (!ctx || !cfg || !xi || !yi || !score) return QG_ERR_INVALID;
   return qg_viterbi_impl (ctx, cfg, n_pairs, xi, yi, want_path, 0, score, x_start, x_end, path_out, path_offsets);
 }
@@ -1178,6 +1183,7 @@ extern "C" int qg_viterbi (qg_ctx* ctx, const qg_dpconfig* cfg, size_t n_pairs, 
 extern "C" int qg_align_reads_range (qg_ctx* ctx, const qg_dpconfig* cfg, size_t first_read, size_t n_reads, const double* null_loglike,
                                      uint32_t* best_ref, double* score, uint32_t* x_start, uint32_t* x_end,
                                      uint8_t** path_out, uint64_t* path_offsets) {
+  if (ctx) cudaSetDevice (ctx->device);                    // the caller may be a host thread that never selected this context's GPU
   if (!ctx || !cfg || !null_loglike || !best_ref || !score || !x_start || !x_end || !path_out || !path_offsets) return QG_ERR_INVALID;
   QG_TRY (qg_check_ready (ctx, cfg));
   const size_t nx = ctx->seqs[QG_REFS].n, ny = n_reads;
@@ -1218,6 +1224,7 @@ extern "C" int qg_align_reads_range (qg_ctx* ctx, const qg_dpconfig* cfg, size_t
 extern "C" int qg_align_reads (qg_ctx* ctx, const qg_dpconfig* cfg, const double* null_loglike,
                                uint32_t* best_ref, double* score, uint32_t* x_start, uint32_t* x_end,
                                uint8_t** path_out, uint64_t* path_offsets) {
+  if (ctx) cudaSetDevice (ctx->device);                    // the caller may be a host thread that never selected this context's GPU
   if (!ctx) return QG_ERR_INVALID;
   return qg_align_reads_range (ctx, cfg, 0, ctx->seqs[QG_READS].n, null_loglike, best_ref, score, x_start, x_end, path_out, path_offsets);
 }
@@ -1274,6 +1281,7 @@ static int qg_launch_prob (qg_ctx* ctx, const qg_dp_plan& plan, qg_prob_args a, 
 
 // ---- Forward --------------------------------------------------------------------------------------------------------
 extern "C" int qg_forward (qg_ctx* ctx, const qg_dpconfig* cfg, size_t n_pairs, const uint32_t* xi, const uint32_t* yi, double* loglike) {
+  if (ctx) cudaSetDevice (ctx->device);                    // the caller may be a host thread that never selected this context's GPU
   if (!ctx || !cfg || !xi || !yi || !loglike) return QG_ERR_INVALID;
   QG_TRY (qg_check_ready (ctx, cfg));
   qg_env_result er;
@@ -1369,6 +1377,7 @@ static int qg_launch_backward (qg_ctx* ctx, const qg_dp_plan& plan, qg_fill_args
 extern "C" int qg_backward_counts (qg_ctx* ctx, const qg_dpconfig* cfg, size_t n_pairs, const uint32_t* xi, const uint32_t* yi,
                                    const double* weights, double* fwd_loglike, double* back_loglike,
                                    double* counts_sum, double* counts_per_pair) {
+  if (ctx) cudaSetDevice (ctx->device);                    // the caller may be a host thread that never selected this context's GPU
   if (!ctx || !cfg || !xi || !yi) return QG_ERR_INVALID;
   QG_TRY (qg_check_ready (ctx, cfg));
   const qg_seqset& Y = ctx->seqs[QG_READS];
@@ -1525,6 +1534,7 @@ static double qg_host_lse (const std::vector<double>& tab, double a, double b) {
 extern "C" int qg_estep (qg_ctx* ctx, const qg_dpconfig* cfg, int use_null, const double* null_loglike,
                          uint32_t* sort_order, uint32_t* sort_len, double* y_loglike,
                          double* param_counts, double* loglike_sum) {
+  if (ctx) cudaSetDevice (ctx->device);                    // the caller may be a host thread that never selected this context's GPU
   if (!ctx || !cfg || !sort_order || !sort_len || !y_loglike || !param_counts || !loglike_sum) return QG_ERR_INVALID;
   if (use_null && !null_loglike) QG_FAIL (ctx, QG_ERR_INVALID, "qg_estep: use_null without null_loglike");
   QG_TRY (qg_check_ready (ctx, cfg));
@@ -1588,6 +1598,7 @@ extern "C" int qg_estep (qg_ctx* ctx, const qg_dpconfig* cfg, int use_null, cons
 
 // ---- overlap ---------------------------------------------------------------------------------------------------------
 extern "C" int qg_set_overlap_model (qg_ctx* ctx, const qg_overlap_model* m) {
+  if (ctx) cudaSetDevice (ctx->device);                    // the caller may be a host thread that never selected this context's GPU
   if (!ctx || !m) return QG_ERR_INVALID;
   if (m->match_k < 1 || m->match_k > 2 || m->gap_k < 0 || m->gap_k > 4)
     QG_FAIL (ctx, QG_ERR_UNSUPPORTED, "overlap model orders K=%d G=%d: this build tabulates the pair emission for K <= 2 (the table grows as 16^K * 94^2 doubles)", m->match_k, m->gap_k);
@@ -1676,6 +1687,7 @@ static int qg_launch_overlap_fill (qg_ctx* ctx, const qg_dp_plan& plan, qg_ofill
 extern "C" int qg_overlap_viterbi (qg_ctx* ctx, const qg_dpconfig* cfg, size_t n_pairs, const uint32_t* xi, const uint32_t* yi,
                                    const uint8_t* y_complemented, const uint8_t* want_path,
                                    double* score, uint32_t* coords4, uint8_t** path_out, uint64_t* path_offsets) {
+  if (ctx) cudaSetDevice (ctx->device);                    // the caller may be a host thread that never selected this context's GPU
   if (!ctx || !cfg || !xi || !yi || !y_complemented || !score) return QG_ERR_INVALID;
   if (!ctx->omodel.set) QG_FAIL (ctx, QG_ERR_STATE, "no overlap model: call qg_set_overlap_model first");
   const qg_seqset& Y = ctx->seqs[QG_READS];
@@ -1854,6 +1866,7 @@ extern "C" int qg_overlap_rows (const uint8_t* x_tok, const uint8_t* y_tok, cons
 extern "C" int qg_overlap_reads (qg_ctx* ctx, const qg_dpconfig* cfg, size_t n_originals, const double* null_loglike,
                                  size_t* n_pairs_out, uint32_t** xi_out, uint32_t** yi_out,
                                  double** score_out, uint32_t** coords4_out, uint8_t** path_out, uint64_t** path_offsets_out) {
+  if (ctx) cudaSetDevice (ctx->device);                    // the caller may be a host thread that never selected this context's GPU
   if (!ctx || !cfg || !null_loglike || !n_pairs_out || !xi_out || !yi_out || !score_out || !coords4_out || !path_out || !path_offsets_out) return QG_ERR_INVALID;
   const size_t N = ctx->seqs[QG_READS].n;
   if (n_originals > N) QG_FAIL (ctx, QG_ERR_INVALID, "n_originals exceeds the read set");
