@@ -143,3 +143,22 @@ def test_emu_general_seeding_path(emu, oracle, workload, monkeypatch):
     pc.check_envelopes(emu, oracle, x, reads, api.dp_config(kmer_threshold=-1, max_size=300_000), xi, yi)
     monkeypatch.setenv("QG_COUNT_BUDGET_MB", "0")     # one pair per sub-batch
     pc.check_envelopes(emu, oracle, x, reads, api.dp_config(kmer_threshold=6), xi, yi)
+
+
+def test_emu_viterbi_matrix_edges(emu_lib, oracle):
+    """bands that run into the matrix edges (reference barely longer / shorter than the read): the phase-split Viterbi
+    kernel's steady state must start and stop exactly where every real cell is inside 1 <= i <= xLen; runs of 1..4
+    diagonals go through the thread-per-run kernel"""
+    qp = pc.default_params()
+    s_or = oracle.scores(qp)
+    g = api.QuaffGPU(lib_path=emu_lib)
+    try:
+        for ref_len, read_len, seed in ((330, 300, 41), (260, 300, 42), (600, 120, 43)):
+            x, reads = pc.make_workload(ref_len=ref_len, n_reads=2, read_len=read_len, seed=seed)
+            g.set_refs(x); g.set_reads(reads); g.set_params(qp)
+            xi, yi = pc.all_pairs(len(x), len(reads))
+            for cfg in (api.dp_config(kmer_threshold=3, band_size=40), api.dp_config(kmer_threshold=2, band_size=2),
+                        api.dp_config(kmer_threshold=4, band_size=90, local=False)):
+                pc.check_viterbi(g, oracle, x, reads, s_or, cfg, xi, yi)
+    finally:
+        g.close()

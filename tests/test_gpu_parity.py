@@ -220,3 +220,16 @@ def test_long_read_seeding(gpu, oracle):
     pc.check_envelopes(gpu, oracle, x, reads, api.dp_config(), xi, yi)
     v = gpu.viterbi(api.dp_config(), xi, yi)
     assert np.isfinite(v["score"]).any()
+
+
+def test_viterbi_matrix_edges_and_narrow_runs(gpu, oracle):
+    """bands clipped by the matrix edges and runs of 1..4 diagonals (thread-per-run kernel): bit-exact paths"""
+    qp = pc.default_params()
+    s_or = oracle.scores(qp)
+    for ref_len, read_len, seed in ((4300, 4000, 41), (3500, 4000, 42), (9000, 1500, 43)):
+        x, reads = pc.make_workload(ref_len=ref_len, n_reads=2, read_len=read_len, seed=seed)
+        gpu.set_refs(x); gpu.set_reads(reads); gpu.set_params(qp)
+        xi, yi = pc.all_pairs(len(x), len(reads))
+        for cfg in (api.dp_config(kmer_threshold=8, band_size=40), api.dp_config(kmer_threshold=5, band_size=2),
+                    api.dp_config(kmer_threshold=10, band_size=90, local=False)):
+            pc.check_viterbi(gpu, oracle, x, reads, s_or, cfg, xi, yi)
