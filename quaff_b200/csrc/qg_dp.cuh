@@ -428,14 +428,16 @@ qg_traceback_warp_kernel (const qg_pair_dp* __restrict__ pairs, uint32_t npairs,
     }
     __syncwarp ();
     if (lane == 0 && state != 0 && !fail) {
+      // (vl, c) = lane and cell of the current diagonal, kept incrementally: Match stays on the diagonal, Insert moves to
+      // d + 1, Delete to d - 1 (no division in the dependent chain)
+      int slot = (i - j) - sg.dlo;
+      int vl = slot / R, c = slot - vl * R;
+      const int width = (int) sg.width;
       while (state != 0) {
-        const int d = i - j;
-        const int slot = d - sg.dlo;
-        if (slot < 0 || slot >= (int) sg.width) { fail = 1; break; }       // cannot happen: paths do not cross the halo
-        const int vl = slot / R, c = slot - vl * R;
+        if (slot < 0 || slot >= width) { fail = 1; break; }                 // cannot happen: paths do not cross the halo
         const int u = j + vl;
         uint32_t word;
-        if (narrow) word = trace[sg.trace_off + (uint64_t) j] >> (4 * (slot - c));
+        if (narrow) word = trace[sg.trace_off + (uint64_t) j];
         else if (multi) word = trace[sg.trace_off + (uint64_t) u * (32 * sg.nwarps) + vl];
         else {
           if (u < u_top - 31) break;                                       // next tile
@@ -449,9 +451,11 @@ qg_traceback_warp_kernel (const qg_pair_dp* __restrict__ pairs, uint32_t npairs,
           state = (src == 0) ? 1 : (src == 1) ? 2 : (src == 2) ? 3 : 0;
         } else if (state == 2) {
           buf[pd.path_cap - 1 - n] = QG_OP_INSERT; ++n; --j;
+          ++slot; if (++c == R) { c = 0; ++vl; }
           state = (nib & 4u) ? 2 : 1;
         } else {
           buf[pd.path_cap - 1 - n] = QG_OP_DELETE; ++n; --i;
+          --slot; if (--c < 0) { c = R - 1; --vl; }
           state = (nib & 8u) ? 3 : 1;
         }
         if (i < 0 || j < 0) { fail = 3; break; }
