@@ -63,9 +63,16 @@ __device__ __forceinline__ int qg_exponent (double v) {      // floor(log2 v) fo
 // read that truncation is worth ~0.1 nat, far more than the 1e-3 nats parity bar, so it is reproduced here.
 #define QG_LSE_CUT 4.5399929762484854e-05                    /* exp(-10) */
 __device__ __forceinline__ double qg_psum (double a, double b) {
-  const double hi = fmax (a, b), lo = fmin (a, b);
+  // one compare orders the pair (fmax + fmin cost twice as many instructions); a, b >= 0, never NaN
+  const bool agtb = a > b;
+  const double hi = agtb ? a : b, lo = agtb ? b : a;
   return (lo <= hi * QG_LSE_CUT) ? hi : hi + lo;
 }
+// high word of a non-negative double: ordered like the value itself (up to the low word), 0 only for 0 / denormals
+__device__ __forceinline__ int qg_hi (double v) { return (int) (__double_as_longlong (v) >> 32); }
+__device__ __forceinline__ int qg_imax (int a, int b) { return a > b ? a : b; }
+#define QG_HI_1EM90 0x2D400000                              /* below ~2^-299 */
+#define QG_HI_1EP90 0x52A00000                              /* above ~2^299  */
 
 struct qg_prob_args {
   const qg_segment* segs;
@@ -125,7 +132,6 @@ qg_forward_prob_kernel (const qg_prob_args a) {
     if (startRow && zero && lM == 0 && lD == 0) ex = 0;
     const double startv = startRow ? qg_pow2 (-ex) : 0.0;
     double rM = 0, rI = 0;
-    double mx = 0;
 
 #pragma unroll
     for (int c = 0; c < R; ++c) {
@@ -137,11 +143,11 @@ qg_forward_prob_kernel (const qg_prob_args a) {
         int exR = __shfl_down_sync (QG_FULL_MASK, ex, 1);
         if (lane == 31) { rM = 0; rI = 0; }
         if (rM != 0 || rI != 0) {
-          bool mine = false;
+          int any = 0;
 #pragma unroll
-          for (int c2 = 0; c2 < R; ++c2) mine = mine || (M[c2] != 0) || (I[c2] != 0) || (D[c2] != 0);
-          if (!mine) ex = exR;
-          else if (exR > ex) { const double f = qg_pow2 (ex - exR); QG_RESCALE_ALL (f); mx *= f; ex = exR; }
+          for (int c2 = 0; c2 < R; ++c2) any |= qg_hi (M[c2]) | qg_hi (I[c2]) | qg_hi (D[c2]);
+          if (any == 0) ex = exR;
+          else if (exR > ex) { const double f = qg_pow2 (ex - exR); QG_RESCALE_ALL (f); ex = exR; }
           const double g = qg_pow2 (exR - ex);
           rM *= g; rI *= g;
         }
@@ -162,12 +168,14 @@ qg_forward_prob_kernel (const qg_prob_args a) {
       double nD = qg_psum (dD * d2d, dM * P.pm2d);
       if (!ok) { nM = 0; nI = 0; nD = 0; }
       M[c] = nM; I[c] = nI; D[c] = nD;
-      mx = fmax (mx, fmax (nM, fmax (nI, nD)));
     }
-    // ---- renormalise this lane if its values drifted
-    zero = (mx == 0);
-    if (!zero && (mx < 1e-90 || mx > 1e90)) {
-      const int k = qg_exponent (mx);
+    // ---- renormalise this lane if its values drifted (largest value by its high word: all values are >= 0)
+    int mxh = 0;
+#pragma unroll
+    for (int c = 0; c < R; ++c) mxh = qg_imax (mxh, qg_imax (qg_hi (M[c]), qg_imax (qg_hi (I[c]), qg_hi (D[c]))));
+    zero = (mxh == 0);
+    if (!zero && (mxh < QG_HI_1EM90 || mxh > QG_HI_1EP90)) {
+      const int k = (mxh >> 20) - 1023;
       const double f = qg_pow2 (-k);
       QG_RESCALE_ALL (f);
       ex += k;
@@ -308,7 +316,6 @@ qg_backward_prob_kernel (const qg_prob_args a) {
     const int exF = (active && zok) ? stex_cur : 0;
     double K = rzm * qg_pow2 (exF + ex - ze);               // count = f * candidate * K (true scale)
     double rI = 0;
-    double mx = 0;
     double nBM[R], nBI[R];
 #pragma unroll
     for (int c = 0; c < R; ++c) {
@@ -318,15 +325,15 @@ qg_backward_prob_kernel (const qg_prob_args a) {
         const int exR = __shfl_down_sync (QG_FULL_MASK, ex, 1);
         if (lane == 31) rI = 0;
         if (rI != 0) {
-          bool mine = (lD != 0);
+          int any = qg_hi (lD);
 #pragma unroll
-          for (int c2 = 0; c2 < R; ++c2) mine = mine || (M[c2] != 0) || (I[c2] != 0) || (c2 < c && (nBM[c2] != 0 || nBI[c2] != 0 || D[c2] != 0));
-          if (!mine) ex = exR;
+          for (int c2 = 0; c2 < R; ++c2) { any |= qg_hi (M[c2]) | qg_hi (I[c2]); if (c2 < c) any |= qg_hi (nBM[c2]) | qg_hi (nBI[c2]) | qg_hi (D[c2]); }
+          if (any == 0) ex = exR;
           else if (exR > ex) {
             const double f = qg_pow2 (ex - exR);
 #pragma unroll
             for (int c2 = 0; c2 < R; ++c2) { M[c2] *= f; I[c2] *= f; if (c2 < c) { nBM[c2] *= f; nBI[c2] *= f; D[c2] *= f; } }
-            lD *= f; mx *= f; ex = exR;
+            lD *= f; ex = exR;
           }
           rI *= qg_pow2 (exR - ex);
           K = rzm * qg_pow2 (exF + ex - ze);
@@ -373,13 +380,15 @@ qg_backward_prob_kernel (const qg_prob_args a) {
         }
       }
       nBM[c] = BM; nBI[c] = BI; D[c] = BD;
-      mx = fmax (mx, fmax (BM, fmax (BI, BD)));
     }
 #pragma unroll
     for (int c = 0; c < R; ++c) { M[c] = nBM[c]; I[c] = nBI[c]; }
-    zero = (mx == 0);
-    if (!zero && (mx < 1e-90 || mx > 1e90)) {
-      const int k = qg_exponent (mx);
+    int mxh = 0;
+#pragma unroll
+    for (int c = 0; c < R; ++c) mxh = qg_imax (mxh, qg_imax (qg_hi (M[c]), qg_imax (qg_hi (I[c]), qg_hi (D[c]))));
+    zero = (mxh == 0);
+    if (!zero && (mxh < QG_HI_1EM90 || mxh > QG_HI_1EP90)) {
+      const int k = (mxh >> 20) - 1023;
       const double f = qg_pow2 (-k);
       QG_RESCALE_ALL (f);
       ex += k;
