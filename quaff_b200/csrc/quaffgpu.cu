@@ -1388,7 +1388,7 @@ extern "C" int qg_backward_counts (qg_ctx* ctx, const qg_dpconfig* cfg, size_t n
   QG_TRY (qg_envelope_stage (ctx, cfg, 48, QG_REFS, n_pairs, xi, yi, er));
   size_t freeb = 0, totb = 0;
   QG_CUDA (ctx, cudaMemGetInfo (&freeb, &totb));
-  const uint64_t budget = (uint64_t) qg_env_size ("QG_STORE_BUDGET_MB", std::min<size_t> (freeb / 2, (size_t) 48 << 30) >> 20) << 20;
+  const uint64_t budget = (uint64_t) qg_env_size ("QG_STORE_BUDGET_MB", std::min<size_t> (freeb / 2, (size_t) 96 << 30) >> 20) << 20;
   qg_dbuf& dSum = ctx->scratch[SC_OUT3];
   QG_TRY (qg_reserve (ctx, dSum, sizeof (double) * (nC + 1)));
   QG_CUDA (ctx, cudaMemsetAsync (dSum.p, 0, sizeof (double) * nC, ctx->stream));
