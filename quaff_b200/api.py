@@ -449,6 +449,46 @@ class QuaffGPUPool:
             return g.align_reads(cfg, null_ll[lo:hi], first=first, count=count, split_paths=False)
         return self._merge(self._each(run))
 
+    def align_batches(self, cfg: DPConfig, steps):
+        """steps: list of (resident batch index, its null_ll).  Each context works through its share of every step on its own
+        (no join between steps: the contexts drift apart and keep the GPU busy while the others do host work); returns
+        one merged result per step."""
+        steps = [(b, np.ascontiguousarray(nl, dtype=np.float64)) for b, nl in steps]
+
+        def run(k, g):
+            outs = []
+            for b, nl in steps:
+                first, count, lo, hi = self.batch_ranges[b][k]
+                outs.append(g.align_reads(cfg, nl[lo:hi], first=first, count=count, split_paths=False))
+            return outs
+        per_ctx = self._each(run)
+        return [self._merge([per_ctx[k][t] for k in range(len(self.ctxs))]) for t in range(len(steps))]
+
+    def align_stream(self, cfg: DPConfig, steps):
+        """steps: list of (tok, qual, off, null_ll) HOST buffers.  Each context uploads its share of a step's reads and aligns
+        them, step after step, independently of the other contexts; returns one merged result per step."""
+        w = len(self.ctxs)
+        prepared = []
+        for tok, qual, off, nl in steps:
+            n = len(off) - 1
+            base, extra = divmod(n, w)
+            bounds = []; lo = 0
+            for k in range(w):
+                hi = lo + base + (1 if k < extra else 0); bounds.append((lo, hi)); lo = hi
+            prepared.append((tok, qual, off, np.ascontiguousarray(nl, dtype=np.float64), bounds))
+
+        def run(k, g):
+            outs = []
+            for tok, qual, off, nl, bounds in prepared:
+                lo, hi = bounds[k]
+                o = off[lo:hi + 1]
+                b0, b1 = int(o[0]), int(o[-1])
+                g.set_seqs_raw(QG_READS, tok[b0:b1], None if qual is None else qual[b0:b1], o - o[0])
+                outs.append(g.align_reads(cfg, nl[lo:hi], split_paths=False))
+            return outs
+        per_ctx = self._each(run)
+        return [self._merge([per_ctx[k][t] for k in range(w)]) for t in range(len(steps))]
+
     def align_reads(self, cfg: DPConfig, null_ll: np.ndarray):
         """seam A over everything uploaded with set_reads / set_reads_raw"""
         null_ll = np.ascontiguousarray(null_ll, dtype=np.float64)

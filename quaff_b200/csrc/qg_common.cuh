@@ -118,6 +118,7 @@ struct qg_ctx {
   // scratch, grown on demand and reused across calls
   qg_dbuf scratch[40];
   int fb_exact = 0;                  // QG_OPT_FB_EXACT
+  cudaEvent_t ev_sync = nullptr;     // blocking host waits (qg_sync)
   void* h_pinned = nullptr;          // pinned staging for large device-to-host copies
   size_t h_pinned_cap = 0;
 };

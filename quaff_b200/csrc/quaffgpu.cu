@@ -25,6 +25,13 @@ enum {
 };
 
 // ---- small helpers -----------------------------------------------------------------------------------
+// Host waits sleep on a blocking event instead of spinning in cudaStreamSynchronize: several contexts (host threads) share
+// one GPU, and spinning waiters burn the cores (and any CPU quota) the other contexts' host work needs.
+static cudaError_t qg_sync (qg_ctx* ctx) {
+  cudaError_t e = cudaEventRecord (ctx->ev_sync, ctx->stream);
+  if (e != cudaSuccess) return e;
+  return cudaEventSynchronize (ctx->ev_sync);
+}
 static int qg_upload (qg_ctx* ctx, qg_dbuf& b, const void* src, size_t bytes) {
   QG_TRY (qg_reserve (ctx, b, bytes));
   if (bytes) QG_CUDA (ctx, cudaMemcpyAsync (b.p, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
@@ -39,12 +46,12 @@ static int qg_download (qg_ctx* ctx, void* dst, const void* src, size_t bytes) {
       ctx->h_pinned_cap = bytes + bytes / 4;
     }
     QG_CUDA (ctx, cudaMemcpyAsync (ctx->h_pinned, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
-    QG_CUDA (ctx, cudaStreamSynchronize (ctx->stream));
+    QG_CUDA (ctx, qg_sync (ctx));
     memcpy (dst, ctx->h_pinned, bytes);
     return QG_OK;
   }
   if (bytes) QG_CUDA (ctx, cudaMemcpyAsync (dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
-  QG_CUDA (ctx, cudaStreamSynchronize (ctx->stream));
+  QG_CUDA (ctx, qg_sync (ctx));
   return QG_OK;
 }
 static int qg_check_launch (qg_ctx* ctx, const char* what) {
@@ -117,8 +124,9 @@ extern "C" int qg_create (qg_ctx** out, int device) {
   ctx->sm_count = prop.multiProcessorCount;
   ctx->smem_optin = prop.sharedMemPerBlockOptin > 2048 ? prop.sharedMemPerBlockOptin - 1024 : prop.sharedMemPerBlockOptin;   // dynamic budget: leave room for the kernels' static shared memory
   if ((e = cudaStreamCreateWithFlags (&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail ("cudaStreamCreate", e);
-  if ((e = cudaEventCreate (&ctx->ev[0])) != cudaSuccess) return fail ("cudaEventCreate", e);
-  if ((e = cudaEventCreate (&ctx->ev[1])) != cudaSuccess) return fail ("cudaEventCreate", e);
+  if ((e = cudaEventCreateWithFlags (&ctx->ev[0], cudaEventBlockingSync)) != cudaSuccess) return fail ("cudaEventCreate", e);
+  if ((e = cudaEventCreateWithFlags (&ctx->ev[1], cudaEventBlockingSync)) != cudaSuccess) return fail ("cudaEventCreate", e);
+  if ((e = cudaEventCreateWithFlags (&ctx->ev_sync, cudaEventBlockingSync | cudaEventDisableTiming)) != cudaSuccess) return fail ("cudaEventCreate", e);
   if ((e = cudaEventCreateWithFlags (&ctx->ev_fork, cudaEventDisableTiming)) != cudaSuccess) return fail ("cudaEventCreate", e);
   for (int i = 0; i < 8; ++i) {
     if ((e = cudaStreamCreateWithFlags (&ctx->side[i], cudaStreamNonBlocking)) != cudaSuccess) return fail ("cudaStreamCreate", e);
@@ -130,7 +138,7 @@ extern "C" int qg_create (qg_ctx** out, int device) {
     std::vector<double> tab (n + 1);
     for (int t = 0; t < n; ++t) { const double x = t * .0001; tab[t] = log (1. + exp (-x)); }
     tab[n] = 0;
-    if (qg_upload (ctx, ctx->d_lse, tab.data (), sizeof (double) * (n + 1)) != QG_OK || cudaStreamSynchronize (ctx->stream) != cudaSuccess) {
+    if (qg_upload (ctx, ctx->d_lse, tab.data (), sizeof (double) * (n + 1)) != QG_OK || qg_sync (ctx) != cudaSuccess) {
       g_create_error = ctx->err; delete ctx; return QG_ERR_CUDA; }
   }
   *out = ctx;
@@ -141,7 +149,7 @@ extern "C" void qg_destroy (qg_ctx* ctx) {
   if (ctx) cudaSetDevice (ctx->device);                    // the caller may be a host thread that never selected this context's GPU
   if (!ctx) return;
   cudaSetDevice (ctx->device);
-  cudaStreamSynchronize (ctx->stream);
+  qg_sync (ctx);
   auto rel = [] (qg_dbuf& b) { if (b.p) cudaFree (b.p); b.p = nullptr; b.cap = 0; };
   for (auto& s : ctx->seqs) { rel (s.d_tok); rel (s.d_qual); rel (s.d_off); rel (s.d_packed); rel (s.d_poff); rel (s.d_codes); }
   rel (ctx->model.d_match); rel (ctx->model.d_insert); rel (ctx->model.d_gap);
@@ -151,7 +159,7 @@ extern "C" void qg_destroy (qg_ctx* ctx) {
   if (ctx->h_pinned) cudaFreeHost (ctx->h_pinned);
   for (auto& b : ctx->scratch) rel (b);
   cudaEventDestroy (ctx->ev[0]); cudaEventDestroy (ctx->ev[1]);
-  cudaEventDestroy (ctx->ev_fork);
+  cudaEventDestroy (ctx->ev_fork); if (ctx->ev_sync) cudaEventDestroy (ctx->ev_sync);
   for (int i = 0; i < 8; ++i) { cudaStreamDestroy (ctx->side[i]); cudaEventDestroy (ctx->ev_join[i]); }
   cudaStreamDestroy (ctx->stream);
   delete ctx;
@@ -215,7 +223,7 @@ extern "C" int qg_set_seqs (qg_ctx* ctx, int which, size_t n, const uint8_t* tok
                s.d_tok.as<uint8_t> (), s.d_off.as<uint64_t> (), s.d_poff.as<uint64_t> (), (uint32_t) n, w, s.d_packed.as<uint64_t> ());
     QG_TRY (qg_check_launch (ctx, "qg_pack_kernel"));
   }
-  QG_CUDA (ctx, cudaStreamSynchronize (ctx->stream));
+  QG_CUDA (ctx, qg_sync (ctx));
   return QG_OK;
 }
 
@@ -245,7 +253,7 @@ extern "C" int qg_set_align_model (qg_ctx* ctx, const qg_align_model* m) {
   for (uint64_t g = 0; g < d.nG; ++g) { gap[g] = m->m2m[g]; gap[d.nG + g] = m->m2i[g]; gap[2 * d.nG + g] = m->m2d[g]; gap[3 * d.nG + g] = m->m2e[g]; }
   QG_TRY (qg_upload (ctx, d.d_gap, gap.data (), sizeof (double) * gap.size ()));
   d.d2d = m->d2d; d.d2m = m->d2m; d.i2i = m->i2i; d.i2m = m->i2m;
-  QG_CUDA (ctx, cudaStreamSynchronize (ctx->stream));
+  QG_CUDA (ctx, qg_sync (ctx));
   d.set = true;
   return QG_OK;
 }
@@ -347,7 +355,7 @@ static int qg_build_read_index (qg_ctx* ctx, int k, const std::vector<qg_index_j
              ctx->scratch[SC_YC64].as<unsigned long long> (), ctx->scratch[SC_KEYS0].as<unsigned long long> (), ctx->scratch[SC_VALS0].as<uint32_t> ());
   QG_TRY (qg_check_launch (ctx, "qg_index_fill_kernel"));
 #ifdef QG_EMU
-  QG_CUDA (ctx, cudaStreamSynchronize (ctx->stream));
+  QG_CUDA (ctx, qg_sync (ctx));
   {
     const unsigned long long* k0 = ctx->scratch[SC_KEYS0].as<unsigned long long> (); const uint32_t* v0 = ctx->scratch[SC_VALS0].as<uint32_t> ();
     unsigned long long* k1 = ctx->scratch[SC_KEYS1].as<unsigned long long> (); uint32_t* v1 = ctx->scratch[SC_VALS1].as<uint32_t> ();
@@ -1511,7 +1519,7 @@ extern "C" int qg_backward_counts (qg_ctx* ctx, const qg_dpconfig* cfg, size_t n
     p0 = p1;
   }
   if (counts_sum) { qg_timer tm (ctx, &ctx->stats.ms_d2h); QG_TRY (qg_download (ctx, counts_sum, dSum.p, sizeof (double) * nC)); }
-  QG_CUDA (ctx, cudaStreamSynchronize (ctx->stream));
+  QG_CUDA (ctx, qg_sync (ctx));
   return QG_OK;
 }
 
@@ -1635,7 +1643,7 @@ extern "C" int qg_set_overlap_model (qg_ctx* ctx, const qg_overlap_model* m) {
   QG_TRY (qg_upload (ctx, d.d_m2m, m2m.data (), sizeof (double) * nG * nG));
   QG_TRY (qg_upload (ctx, d.d_m2i, m2i.data (), sizeof (double) * nG * nG));
   QG_TRY (qg_upload (ctx, d.d_m2d, m2d.data (), sizeof (double) * nG * nG));
-  QG_CUDA (ctx, cudaStreamSynchronize (ctx->stream));
+  QG_CUDA (ctx, qg_sync (ctx));
   d.built[0] = d.built[1] = false;
   d.set = true;
   return QG_OK;

@@ -174,7 +174,7 @@ static inline cudaError_t cudaStreamCreate (cudaStream_t* s) { *s = 0; return cu
 static inline cudaError_t cudaStreamDestroy (cudaStream_t) { return cudaSuccess; }
 static inline cudaError_t cudaStreamSynchronize (cudaStream_t) { return cudaSuccess; }
 static inline cudaError_t cudaStreamWaitEvent (cudaStream_t, cudaEvent_t, unsigned = 0) { return cudaSuccess; }
-enum { cudaEventDisableTiming = 2 };
+enum { cudaEventDisableTiming = 2, cudaEventBlockingSync = 1 };
 static inline cudaError_t cudaEventCreateWithFlags (cudaEvent_t* e, unsigned) { *e = new qgemu_event (); return cudaSuccess; }
 static inline cudaError_t cudaDeviceSynchronize () { return cudaSuccess; }
 static inline cudaError_t cudaEventCreate (cudaEvent_t* e) { *e = new qgemu_event (); return cudaSuccess; }
