@@ -186,7 +186,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the Forward/Backward side measurement")
     ap.add_argument("--ref-all-steps", action="store_true")
-    ap.add_argument("--contexts", type=int, default=2, help="contexts (host thread + stream each) per GPU")
+    ap.add_argument("--contexts", type=int, default=4, help="contexts (host thread + stream each) per GPU")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl != "reference":
         args.warmup = max(args.warmup, 3) if os.environ.get("QB_ALLOW_SHORT_WARMUP") is None else args.warmup

@@ -28,6 +28,8 @@ enum {
 // Host waits sleep on a blocking event instead of spinning in cudaStreamSynchronize: several contexts (host threads) share
 // one GPU, and spinning waiters burn the cores (and any CPU quota) the other contexts' host work needs.
 static cudaError_t qg_sync (qg_ctx* ctx) {
+  static const bool spin = getenv ("QG_SPIN_SYNC") != nullptr;
+  if (spin) return cudaStreamSynchronize (ctx->stream);
   cudaError_t e = cudaEventRecord (ctx->ev_sync, ctx->stream);
   if (e != cudaSuccess) return e;
   return cudaEventSynchronize (ctx->ev_sync);
