@@ -213,6 +213,64 @@ qg_forward_prob_kernel (const qg_prob_args a) {
   }
 }
 
+// ---- Forward on an isolated diagonal (a run of width 1, e.g. the always-present diagonal 0 of every pair) ------------
+// Its neighbours are halo diagonals, so Insert and Delete stay 0 and Match is one product chain
+// M(j) = (M(j-1) * m2m_j) * E_j, started on row 1.  A warp per such run would spend yLen + 31 macro-steps on one cell per
+// row; one THREAD does the chain here (same multiplications in the same order, power-of-two renormalisation: the same
+// value).  Forward-only calls (the E-step's gate pass); the store for Backward still comes from the warp kernel.
+__global__ void __launch_bounds__ (64)
+qg_forward_prob_diag_kernel (const qg_prob_args a, uint32_t nseg) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nseg) return;
+  const qg_segment sg = a.segs[t];
+  const int xlen = (int) sg.xlen, ylen = (int) sg.ylen, dlo = sg.dlo;
+  const uint64_t* xw = a.xpacked + a.xpoff[sg.xseq];
+  const int nxw = (xlen + 31) >> 5;
+  const qg_rowq* rq = a.rq + sg.rp_off;
+  const bool local = a.local != 0;
+  const double m2e = rq[0].pm2m;
+  double M = 0; int ex = 0;
+  uint64_t win = 0; int pw = 0; bool have_win = false;
+  double pe_ring[4][4], m2m_ring[4];                        // row parameters four rows ahead (one long dependent chain)
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int jr = (1 + k > ylen + 1) ? ylen + 1 : 1 + k;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) pe_ring[k][q] = rq[jr].pe[q];
+    m2m_ring[k] = rq[jr].pm2m;
+  }
+  for (int j0 = 1; j0 <= ylen; j0 += 4) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int j = j0 + k;
+      if (j > ylen) break;
+      const double pe[4] = { pe_ring[k][0], pe_ring[k][1], pe_ring[k][2], pe_ring[k][3] };
+      const double pm2m = m2m_ring[k];
+      {
+        const int jr = (j + 4 > ylen + 1) ? ylen + 1 : j + 4;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) pe_ring[k][q] = rq[jr].pe[q];
+        m2m_ring[k] = rq[jr].pm2m;
+      }
+      const int i = dlo + j, p0 = i - 1;
+      if (!have_win || p0 < pw || p0 + 1 > pw + 32) { win = qg_fetch32 (xw, nxw, p0); pw = p0; have_win = true; }
+      const int tk = (int) ((win >> (2 * ((p0 - pw) & 31))) & 3);
+      const bool ok = (i >= 1) && (i <= xlen);
+      double nM = M * pm2m;
+      if (j == 1 && (i == 1 || local)) nM = qg_psum (nM, 1.0);             // ex == 0 on the start row
+      nM *= qg_sel4 (pe, tk);
+      if (!ok) nM = 0;
+      M = nM;
+      const int mh = qg_hi (M);
+      if (mh != 0 && (mh < QG_HI_1EM90 || mh > QG_HI_1EP90)) { const int kk = (mh >> 20) - 1023; M *= qg_pow2 (-kk); ex += kk; }
+    }
+  }
+  const int iend = dlo + ylen;
+  const bool isEnd = (iend >= 1) && (iend <= xlen) && (iend == xlen || local);
+  a.endvals[sg.aux_off] = isEnd ? M * m2e : 0.0;
+  a.endex[sg.aux_off] = ex;
+}
+
 // Forward result per pair: log( sum_slot m * 2^e ) + S_yLen; also the normalised sum (zm, ze) for Backward
 __global__ void qg_forward_prob_finalize_kernel (const qg_pair_dp* __restrict__ pairs, uint32_t npairs, const qg_segment* __restrict__ segs,
                                                  const double* __restrict__ endvals, const int* __restrict__ endex, const double* __restrict__ rs,

@@ -656,7 +656,7 @@ static int qg_pick_R (uint32_t width, int* R, int* nw) {
 
 // pairs [p0, p1) of the call; trace / store sizing according to `mode` (0 Viterbi, 1 Forward, 2 Forward+store)
 static int qg_build_plan (qg_ctx* ctx, const qg_env_result& er, size_t p0, size_t p1, const uint32_t* xi, const uint32_t* yi,
-                          int x_set, int mode, qg_dp_plan& plan) {
+                          int x_set, int mode, qg_dp_plan& plan, bool diag_forward = false) {
   const qg_seqset& X = ctx->seqs[x_set];
   const qg_seqset& Y = ctx->seqs[QG_READS];
   plan = qg_dp_plan ();
@@ -687,6 +687,7 @@ static int qg_build_plan (qg_ctx* ctx, const qg_env_result& er, size_t p0, size_
       const uint64_t lanes = 32ull * nw;
       const bool narrow = mode == 0 && sg.width <= 4 && !getenv ("QG_VIT_GENERIC");    // one thread per run (qg_vit_narrow_kernel)
       if (narrow) { sg.R = sg.width; sg.nwarps = 0; sg.trace_off = plan.trace_words; plan.trace_words += (((uint64_t) pp.ylen + 4) / 4) * 4; }
+      else if (diag_forward && mode == 1 && sg.width == 1) { sg.R = 1; sg.nwarps = 0; }       // one thread per isolated diagonal (qg_forward_prob_diag_kernel)
       else if (mode == 0 || mode == 3) { sg.trace_off = plan.trace_words; plan.trace_words += ((uint64_t) pp.ylen + lanes + 1) * lanes; }
       if (mode == 3) { sg.acc_off = plan.acc_rows; plan.acc_rows += (uint64_t) pp.ylen + 2; }
       if (mode == 2) { sg.store_off = plan.store_doubles; plan.store_doubles += ((uint64_t) pp.ylen + lanes + 1) * 3 * lanes * R;
@@ -1275,6 +1276,11 @@ static int qg_launch_prob (qg_ctx* ctx, const qg_dp_plan& plan, qg_prob_args a, 
   for (const auto& L : plan.launches) {
     cudaStream_t st; QG_TRY (qg_side (ctx, kcls++, &st));
     a.segs = d_segs_launch_order + L.begin;
+    if (L.nw == 0) {                                        // isolated diagonals, Forward only: one thread each
+      QG_LAUNCH (qg_forward_prob_diag_kernel, (L.count + 63) / 64, 64, 0, st, a, L.count);
+      QG_TRY (qg_check_launch (ctx, "qg_forward_prob_diag_kernel"));
+      continue;
+    }
 #define QG_CASE(RR) case RR: \
       if (BACKWARD) { auto kfn = qg_backward_prob_kernel<RR>; QG_LAUNCH (kfn, L.count, 32, 0, st, a); } \
       else { auto kfn = qg_forward_prob_kernel<RR>; QG_LAUNCH (kfn, L.count, 32, 0, st, a); } break;
@@ -1311,7 +1317,9 @@ extern "C" int qg_forward (qg_ctx* ctx, const qg_dpconfig* cfg, size_t n_pairs, 
     }
   }
   qg_dp_plan plan;
-  QG_TRY (qg_build_plan (ctx, er, 0, n_pairs, xi, yi, QG_REFS, 1, plan));
+  QG_TRY (qg_build_plan (ctx, er, 0, n_pairs, xi, yi, QG_REFS, 1, plan, !ctx->fb_exact && !getenv ("QG_VIT_GENERIC")));
+  if (!ctx->fb_exact && !qg_plan_single_warp (plan))        // multi-warp runs use the log-space kernels for the whole call: no thread-per-diagonal class there
+    QG_TRY (qg_build_plan (ctx, er, 0, n_pairs, xi, yi, QG_REFS, 1, plan));
   // Forward folds end values per pair in pair order: keep segs in pair order, launch classes through an index
   for (uint32_t s : plan.order) plan.segs_sorted.push_back (plan.segs[s]);
   {
