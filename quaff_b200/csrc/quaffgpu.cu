@@ -25,6 +25,17 @@ enum {
 };
 
 // ---- small helpers -----------------------------------------------------------------------------------
+// QG_HOST_TRACE=1: host wall-clock between the marked points of an align call, on stderr (diagnostics only)
+#include <chrono>
+static void qg_htrace (const char* label) {
+  static const bool on = getenv ("QG_HOST_TRACE") != nullptr;
+  if (!on) return;
+  static thread_local std::chrono::steady_clock::time_point last = std::chrono::steady_clock::now ();
+  const auto now = std::chrono::steady_clock::now ();
+  fprintf (stderr, "[qg %p] %-14s +%.2f ms\n", (void*) &last, label, std::chrono::duration<double, std::milli> (now - last).count ());
+  last = now;
+}
+
 // Host waits sleep on a blocking event instead of spinning in cudaStreamSynchronize: several contexts (host threads) share
 // one GPU, and spinning waiters burn the cores (and any CPU quota) the other contexts' host work needs.
 static cudaError_t qg_sync (qg_ctx* ctx) {
@@ -1071,8 +1082,10 @@ static int qg_viterbi_impl (qg_ctx* ctx, const qg_dpconfig* cfg, size_t n_pairs,
       if (p1 > p0 && (words + w) * 4 > budget) break;
       words += w; p1 = pe;
     }
+    qg_htrace ("envelopes");
     qg_dp_plan plan;
     QG_TRY (qg_build_plan (ctx, er, p0, p1, xi, yi, QG_REFS, 0, plan));
+    qg_htrace ("plan");
     const size_t np = p1 - p0;
     for (uint32_t s : plan.order) plan.segs_sorted.push_back (plan.segs[s]);
     {
@@ -1091,6 +1104,7 @@ static int qg_viterbi_impl (qg_ctx* ctx, const qg_dpconfig* cfg, size_t n_pairs,
     ctx->stats.trace_bytes += plan.trace_words * 4;
     ctx->stats.n_segments += plan.segs.size ();
     ctx->stats.cell_updates += qg_plan_cells (er, p0, p1);
+    qg_htrace ("prep");
     {
       qg_timer tm (ctx, &ctx->stats.ms_viterbi);
       qg_fill_args a = qg_base_args (ctx, cfg, QG_REFS);
@@ -1106,6 +1120,7 @@ static int qg_viterbi_impl (qg_ctx* ctx, const qg_dpconfig* cfg, size_t n_pairs,
       qg_timer tm (ctx, &ctx->stats.ms_d2h);
       QG_TRY (qg_download (ctx, score + p0, ctx->scratch[SC_OUT0].p, sizeof (double) * np));
     }
+    qg_htrace ("fill+scores");
     if (paths) {
       // which pairs get a traceback
       uint64_t scratch_bytes = 0;
@@ -1206,7 +1221,9 @@ extern "C" int qg_align_reads_range (qg_ctx* ctx, const qg_dpconfig* cfg, size_t
   std::vector<uint32_t> xs (np), xe (np);
   std::vector<uint64_t> poff (np + 1);
   uint8_t* paths = nullptr;
+  qg_htrace ("entry");
   QG_TRY (qg_viterbi_impl (ctx, cfg, np, xi.data (), yi.data (), nullptr, nx, sc.data (), xs.data (), xe.data (), &paths, poff.data ()));
+  qg_htrace ("traceback+out");
   // the traced pair of each read is its best one; compact the path list to one entry per read
   uint64_t total = 0;
   for (size_t y = 0; y < ny; ++y) {
@@ -1229,6 +1246,7 @@ extern "C" int qg_align_reads_range (qg_ctx* ctx, const qg_dpconfig* cfg, size_t
   }
   path_offsets[ny] = total;
   *path_out = paths;
+  qg_htrace ("compact");
   return QG_OK;
 }
 
