@@ -581,7 +581,7 @@ static int qg_envelope_stage_retry (qg_ctx* ctx, const qg_dpconfig* cfg, uint64_
                                     size_t n_pairs, const uint32_t* xi, const uint32_t* yi, qg_env_result& out) {
   const uint32_t half = (uint32_t) cfg->band_size / 2;
   const uint32_t cap_max = 8 * QG_SEED_CHUNK / (2 * half + 2) + 3;
-  uint32_t cap = (uint32_t) qg_env_size ("QG_RUN_CAP", 64);
+  uint32_t cap = (uint32_t) qg_env_size ("QG_RUN_CAP", 16);
   while (true) {
     bool overflow = false;
     QG_TRY (qg_envelope_stage_cap (ctx, cfg, cell_size, x_set, n_pairs, xi, yi, out, cap, &overflow));
