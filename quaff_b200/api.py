@@ -393,6 +393,8 @@ class QuaffGPUPool:
 
         def up(k, g):
             lo, hi = self.bounds[k]
+            if hi == lo:
+                return
             o = off[lo:hi + 1]
             b0, b1 = int(o[0]), int(o[-1])
             g.set_seqs_raw(QG_READS, tok[b0:b1], None if qual is None else qual[b0:b1], o - o[0])
@@ -431,6 +433,11 @@ class QuaffGPUPool:
             g.set_seqs_raw(QG_READS, np.concatenate(t), np.concatenate(q) if q else None, np.concatenate(offs))
         self._each(up)
 
+    @staticmethod
+    def _empty():
+        return dict(best_ref=np.zeros(0, np.uint32), score=np.zeros(0), x_start=np.zeros(0, np.uint32), x_end=np.zeros(0, np.uint32),
+                    paths=np.zeros(0, np.uint8), path_offsets=np.zeros(1, np.uint64))
+
     def _merge(self, parts):
         out = {k: np.concatenate([p[k] for p in parts]) for k in ("best_ref", "score", "x_start", "x_end", "paths")}
         base = np.uint64(0); cat = []
@@ -446,6 +453,8 @@ class QuaffGPUPool:
 
         def run(k, g):
             first, count, lo, hi = self.batch_ranges[b][k]
+            if count == 0:
+                return self._empty()
             return g.align_reads(cfg, null_ll[lo:hi], first=first, count=count, split_paths=False)
         return self._merge(self._each(run))
 
@@ -459,7 +468,7 @@ class QuaffGPUPool:
             outs = []
             for b, nl in steps:
                 first, count, lo, hi = self.batch_ranges[b][k]
-                outs.append(g.align_reads(cfg, nl[lo:hi], first=first, count=count, split_paths=False))
+                outs.append(g.align_reads(cfg, nl[lo:hi], first=first, count=count, split_paths=False) if count else self._empty())
             return outs
         per_ctx = self._each(run)
         return [self._merge([per_ctx[k][t] for k in range(len(self.ctxs))]) for t in range(len(steps))]
@@ -481,6 +490,8 @@ class QuaffGPUPool:
             outs = []
             for tok, qual, off, nl, bounds in prepared:
                 lo, hi = bounds[k]
+                if hi == lo:
+                    outs.append(self._empty()); continue
                 o = off[lo:hi + 1]
                 b0, b1 = int(o[0]), int(o[-1])
                 g.set_seqs_raw(QG_READS, tok[b0:b1], None if qual is None else qual[b0:b1], o - o[0])
@@ -495,6 +506,8 @@ class QuaffGPUPool:
 
         def run(k, g):
             lo, hi = self.bounds[k]
+            if hi == lo:
+                return self._empty()
             return g.align_reads(cfg, null_ll[lo:hi], split_paths=False)
         return self._merge(self._each(run))
 

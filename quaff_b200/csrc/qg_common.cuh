@@ -10,7 +10,7 @@
 #else
 #include <cuda_runtime.h>
 #define QG_LAUNCH(kern, grid, block, smem, stream, ...) \
-  kern<<<dim3 (grid), dim3 (block), (size_t) (smem), (stream)>>> (__VA_ARGS__)
+  do { const dim3 qg_grid_ (grid); if (qg_grid_.x && qg_grid_.y && qg_grid_.z) kern<<<qg_grid_, dim3 (block), (size_t) (smem), (stream)>>> (__VA_ARGS__); } while (0)   /* an empty grid is a no-op, not an error */
 #define QG_DYN_SMEM(name) extern __shared__ __align__ (16) unsigned char name[]
 #endif
 
@@ -116,7 +116,7 @@ struct qg_ctx {
   qg_dbuf d_lse;                     // the 100001-entry FP64 log-sum-exp table (logsumexp.cpp:20-28)
   qg_stats stats;
   // scratch, grown on demand and reused across calls
-  qg_dbuf scratch[40];
+  qg_dbuf scratch[48];
   int fb_exact = 0;                  // QG_OPT_FB_EXACT
   cudaEvent_t ev_sync = nullptr;     // blocking host waits (qg_sync)
   void* h_pinned = nullptr;          // pinned staging for large device-to-host copies

@@ -162,3 +162,27 @@ def test_emu_viterbi_matrix_edges(emu_lib, oracle):
                 pc.check_viterbi(g, oracle, x, reads, s_or, cfg, xi, yi)
     finally:
         g.close()
+
+
+def test_emu_pool_with_more_contexts_than_reads(emu_lib, oracle):
+    """QuaffGPUPool: contexts whose share of the reads is empty contribute empty results"""
+    x, reads = pc.make_workload(ref_len=2000, n_reads=1, read_len=200, seed=3)
+    qp = pc.default_params()
+    cfg = api.dp_config(kmer_threshold=6)
+    g = api.QuaffGPU(lib_path=emu_lib)
+    g.set_refs(x); g.set_reads(reads); g.set_params(qp)
+    one = g.align_reads(cfg, np.zeros(len(reads)))
+    g.close()
+    P = api.QuaffGPUPool(n_ctx=3, lib_path=emu_lib)
+    try:
+        P.set_refs(x); P.set_params(qp); P.set_reads(reads)
+        a = P.align_reads(cfg, np.zeros(len(reads)))
+        assert np.array_equal(a["score"], one["score"]) and np.array_equal(a["best_ref"], one["best_ref"])
+        flat = [api._flatten(reads, True)]
+        P.set_read_batches(flat)
+        b = P.align_batches(cfg, [(0, np.zeros(len(reads)))])[0]
+        c = P.align_stream(cfg, [flat[0] + (np.zeros(len(reads)),)])[0]
+        assert np.array_equal(b["score"], one["score"]) and np.array_equal(c["score"], one["score"])
+        assert np.array_equal(np.concatenate(one["paths"]) if isinstance(one["paths"], list) else one["paths"], b["paths"])
+    finally:
+        P.close()

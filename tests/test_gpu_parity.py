@@ -233,3 +233,18 @@ def test_viterbi_matrix_edges_and_narrow_runs(gpu, oracle):
         for cfg in (api.dp_config(kmer_threshold=8, band_size=40), api.dp_config(kmer_threshold=5, band_size=2),
                     api.dp_config(kmer_threshold=10, band_size=90, local=False)):
             pc.check_viterbi(gpu, oracle, x, reads, s_or, cfg, xi, yi)
+
+
+def test_empty_pair_lists_are_noops(gpu, oracle, workload):
+    """zero pairs: every entry point returns empty results (empty grids are skipped, not launch errors)"""
+    e = np.zeros(0, np.uint32)
+    cfg = api.dp_config(kmer_threshold=14)
+    d, cu = gpu.envelopes(cfg, e, e)
+    assert len(d) == 0 and len(cu) == 0
+    v = gpu.viterbi(cfg, e, e)
+    assert len(v["score"]) == 0 and len(v["paths"]) == 0
+    assert len(gpu.forward(cfg, e, e)) == 0
+    b = gpu.backward_counts(cfg, e, e)
+    assert np.all(np.asarray(b["counts"]) == 0) if "counts" in b else True
+    a = gpu.align_reads(cfg, np.zeros(0), first=0, count=0)
+    assert len(a["score"]) == 0
