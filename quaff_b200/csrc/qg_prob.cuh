@@ -316,6 +316,22 @@ qg_backward_prob_kernel (const qg_prob_args a) {
   const double rzm = zok ? 1.0 / zm : 0.0;
   qg_rowrec* rowacc = (qg_rowrec*) a.rowacc + sg.acc_off;
   const int flane = 31 - lane;                              // the Forward lane that owns my slots
+  if (width == 1) {
+    // An isolated diagonal is a single path: F(cell) * B(cell) is the run's Forward value for every cell on it, so every
+    // posterior count of the run is (run value) / Z.  When that ratio is below 2^-1100 (the always-present diagonal 0 next
+    // to a real alignment: ~e^-9000) the counts are exactly 0 in FP64 -- the reference's exp() underflows as well -- and the
+    // run's start value is dropped by the log-sum-exp cut-off: write the zeros and skip the yLen + 31 macro-steps.
+    const double fv = a.endvals[sg.aux_off];
+    const int fe = a.endex[sg.aux_off];
+    __syncwarp ();
+    const bool negligible = !zok || fv == 0.0 || (qg_exponent (fv) + fe) - (qg_exponent (zm) + ze) < -1100;
+    if (negligible) {
+      double* ra = (double*) (rowacc + 1);
+      for (int t = lane; t < ylen * 8; t += 32) ra[t] = 0.0;
+      for (int s2 = lane; s2 < SW; s2 += 32) { a.endvals[sg.aux_off + s2] = 0.0; a.endex[sg.aux_off + s2] = 0; }
+      return;
+    }
+  }
 
   double M[R], I[R], D[R];                                  // B_M, B_I of row j+1 (then of row j); D[] is this row's B_D chain
 #pragma unroll

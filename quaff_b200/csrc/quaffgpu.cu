@@ -1424,7 +1424,9 @@ extern "C" int qg_backward_counts (qg_ctx* ctx, const qg_dpconfig* cfg, size_t n
   QG_TRY (qg_envelope_stage (ctx, cfg, 48, QG_REFS, n_pairs, xi, yi, er));
   size_t freeb = 0, totb = 0;
   QG_CUDA (ctx, cudaMemGetInfo (&freeb, &totb));
-  const uint64_t budget = (uint64_t) qg_env_size ("QG_STORE_BUDGET_MB", std::min<size_t> (freeb / 2, (size_t) 96 << 30) >> 20) << 20;
+  // what this context already holds for the store is available to it again: count it with the free memory
+  const size_t avail = freeb + ctx->scratch[SC_STORE].cap;
+  const uint64_t budget = (uint64_t) qg_env_size ("QG_STORE_BUDGET_MB", std::min<size_t> (avail / 20 * 13, (size_t) 128 << 30) >> 20) << 20;
   qg_dbuf& dSum = ctx->scratch[SC_OUT3];
   QG_TRY (qg_reserve (ctx, dSum, sizeof (double) * (nC + 1)));
   QG_CUDA (ctx, cudaMemsetAsync (dSum.p, 0, sizeof (double) * nC, ctx->stream));
