@@ -283,6 +283,8 @@ def main():
         G.forward(cfg, xi, yi)
         s1 = G.stats(reset=True)
         sel = xi == xi                                               # Backward for every pair of the slice
+        G.backward_counts(cfg, xi[sel], yi[sel])                     # warm-up: the first call allocates the Forward store
+        G.stats(reset=True)
         G.backward_counts(cfg, xi[sel], yi[sel])
         s2 = G.stats(reset=True)
         cu_f = s1["cell_updates"]; cu_b = s2["cell_updates"] / 2
