@@ -317,22 +317,31 @@ qg_backward_prob_kernel (const qg_prob_args a) {
   qg_rowrec* rowacc = (qg_rowrec*) a.rowacc + sg.acc_off;
   const int flane = 31 - lane;                              // the Forward lane that owns my slots
   if (width == 1) {
-    // An isolated diagonal is a single path: F(cell) * B(cell) is the run's Forward value for every cell on it, so every
-    // posterior count of the run is (run value) / Z.  When that ratio is below 2^-1100 (the always-present diagonal 0 next
-    // to a real alignment: ~e^-9000) the counts are exactly 0 in FP64 -- the reference's exp() underflows as well -- and the
-    // run's start value is dropped by the log-sum-exp cut-off: write the zeros and skip the yLen + 31 macro-steps.
+    // An isolated diagonal is a single path (its neighbours are halo diagonals: Insert and Delete stay 0), so the
+    // posterior of every transition on it is the same number w = (run's Forward value) / Z and Backward is closed form:
+    // every source row j < yLen counts w for Match->Match in context c(j) and w for the emission of row j+1, the end
+    // transition and the start emission count w once.  Next to a real alignment w underflows to exactly 0 (the run is
+    // ~e^-9000 of Z; the reference's exp() underflows as well) and nothing is written (the count rows are pre-zeroed).
+    // The run's Backward start value is its path probability, which is what the Forward kernel left in slot 0.
     const double fv = a.endvals[sg.aux_off];
     const int fe = a.endex[sg.aux_off];
-    __syncwarp ();
-    const bool negligible = !zok || fv == 0.0 || (qg_exponent (fv) + fe) - (qg_exponent (zm) + ze) < -1100;
-    if (negligible) {
-      double* ra = (double*) (rowacc + 1);
-      for (int t = lane; t < ylen * 8; t += 32) ra[t] = 0.0;
-      for (int s2 = lane; s2 < SW; s2 += 32) { a.endvals[sg.aux_off + s2] = 0.0; a.endex[sg.aux_off + s2] = 0; }
-      return;
+    const double w = (zok && fv != 0.0) ? (fv * rzm) * qg_pow2 (fe - ze) : 0.0;
+    if (w != 0.0) {
+      for (int j = 1 + lane; j < ylen; j += 32) {
+        qg_rowrec r;
+        const int tn = qg_tok (xw, nxw, sg.dlo + j);          // x base of the destination cell (i + 1, j + 1), i = dlo + j
+#pragma unroll
+        for (int t = 0; t < 4; ++t) r.cnt[t] = (t == tn) ? w : 0.0;
+        r.ins = 0; r.m2m = w; r.m2i = 0; r.m2d = 0;
+        rowacc[j] = r;
+      }
+      if (lane == 0) {
+        a.seg_scal[12 * sg.seg_id + 4] = w;                                         // m2e
+        a.seg_scal[12 * sg.seg_id + 5 + qg_tok (xw, nxw, sg.dlo)] = w;               // start emission: x base of cell (dlo + 1, 1)
+      }
     }
+    return;
   }
-
   double M[R], I[R], D[R];                                  // B_M, B_I of row j+1 (then of row j); D[] is this row's B_D chain
 #pragma unroll
   for (int c = 0; c < R; ++c) { M[c] = 0; I[c] = 0; D[c] = 0; }

@@ -698,10 +698,10 @@ static int qg_build_plan (qg_ctx* ctx, const qg_env_result& er, size_t p0, size_
       const uint64_t lanes = 32ull * nw;
       const bool narrow = mode == 0 && sg.width <= 4 && !getenv ("QG_VIT_GENERIC");    // one thread per run (qg_vit_narrow_kernel)
       if (narrow) { sg.R = sg.width; sg.nwarps = 0; sg.trace_off = plan.trace_words; plan.trace_words += (((uint64_t) pp.ylen + 4) / 4) * 4; }
-      else if (diag_forward && mode == 1 && sg.width == 1) { sg.R = 1; sg.nwarps = 0; }       // one thread per isolated diagonal (qg_forward_prob_diag_kernel)
+      else if (diag_forward && (mode == 1 || mode == 2) && sg.width == 1) { sg.R = 1; sg.nwarps = 0; }   // isolated diagonal: one thread (qg_forward_prob_diag_kernel), closed-form Backward
       else if (mode == 0 || mode == 3) { sg.trace_off = plan.trace_words; plan.trace_words += ((uint64_t) pp.ylen + lanes + 1) * lanes; }
       if (mode == 3) { sg.acc_off = plan.acc_rows; plan.acc_rows += (uint64_t) pp.ylen + 2; }
-      if (mode == 2) { sg.store_off = plan.store_doubles; plan.store_doubles += ((uint64_t) pp.ylen + lanes + 1) * 3 * lanes * R;
+      if (mode == 2) { if (sg.nwarps != 0) { sg.store_off = plan.store_doubles; plan.store_doubles += ((uint64_t) pp.ylen + lanes + 1) * 3 * lanes * R; }
                        sg.acc_off = plan.acc_rows; plan.acc_rows += (uint64_t) pp.ylen + 2; }
       sg.seg_id = plan.segs.size ();
       if (mode == 0) sg.aux_off = plan.segs.size ();           // Viterbi: index of the segment in pair order
@@ -1294,9 +1294,10 @@ static int qg_launch_prob (qg_ctx* ctx, const qg_dp_plan& plan, qg_prob_args a, 
   for (const auto& L : plan.launches) {
     cudaStream_t st; QG_TRY (qg_side (ctx, kcls++, &st));
     a.segs = d_segs_launch_order + L.begin;
-    if (L.nw == 0) {                                        // isolated diagonals, Forward only: one thread each
-      QG_LAUNCH (qg_forward_prob_diag_kernel, (L.count + 63) / 64, 64, 0, st, a, L.count);
-      QG_TRY (qg_check_launch (ctx, "qg_forward_prob_diag_kernel"));
+    if (L.nw == 0) {                                        // isolated diagonals: one thread each (Forward), closed form (Backward)
+      if (BACKWARD) { auto kfn = qg_backward_prob_kernel<2>; QG_LAUNCH (kfn, L.count, 32, 0, st, a); }
+      else QG_LAUNCH (qg_forward_prob_diag_kernel, (L.count + 63) / 64, 64, 0, st, a, L.count);
+      QG_TRY (qg_check_launch (ctx, BACKWARD ? "qg_backward_prob_kernel (diagonal)" : "qg_forward_prob_diag_kernel"));
       continue;
     }
 #define QG_CASE(RR) case RR: \
@@ -1445,7 +1446,8 @@ extern "C" int qg_backward_counts (qg_ctx* ctx, const qg_dpconfig* cfg, size_t n
     }
     const size_t np = p1 - p0;
     qg_dp_plan plan;
-    QG_TRY (qg_build_plan (ctx, er, p0, p1, xi, yi, QG_REFS, 2, plan));
+    QG_TRY (qg_build_plan (ctx, er, p0, p1, xi, yi, QG_REFS, 2, plan, !ctx->fb_exact && !getenv ("QG_VIT_GENERIC")));
+    if (!ctx->fb_exact && !qg_plan_single_warp (plan)) QG_TRY (qg_build_plan (ctx, er, p0, p1, xi, yi, QG_REFS, 2, plan));   // log-space kernels: no diagonal class
     for (uint32_t s : plan.order) plan.segs_sorted.push_back (plan.segs[s]);
     {
       qg_timer tm (ctx, &ctx->stats.ms_prep);
