@@ -357,7 +357,7 @@ qg_memtier_kernel (const qg_pair_desc* __restrict__ pairs, const uint32_t* __res
   if (fixed_threshold >= 0) {
     // plain -kmatchn threshold on the general path's global counts (diagenv.cpp:62-96 with kmerThreshold >= 0)
     for (int t = tid; t < ndiag; t += blockDim.x)
-      if (cnt[t] >= (uint32_t) fixed_threshold) {
+      if (cnt[t] != 0 && cnt[t] >= (uint32_t) fixed_threshold) {   // only diagonals that received a hit exist in diagKmerCount (diagenv.cpp:33-46)
         const int seed = t - span;
         const int lo = seed - half_band > min_diag ? seed - half_band : min_diag;
         const int hi = seed + half_band < max_diag ? seed + half_band : max_diag;

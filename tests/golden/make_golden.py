@@ -134,8 +134,33 @@ def reference_own_goldens():
     print("c8f30 goldens: align", out["align_score"], "overlap", out["overlap_score"], "default-flags overlap", out["overlap_default"]["score"])
 
 
+def cfg5_case(name="cfg5_full"):
+    """BASELINE config 5 at its stated shape: one 10 kb read against a 50 kb reference, `-kmatchoff -fwdstrand` (full DP,
+    5e8 cells; the reference needs 12 GB for the matrix).  Only the numbers and the run-length path are kept; the inputs are
+    regenerated from the seeds (reference seed 3, reads seed 4)."""
+    from quaff_b200.synth import random_ref, sample_reads
+    ref = random_ref(50_000, 3)
+    reads, starts, strands = sample_reads(ref, 1, 10_000, 4, both_strands=False)
+    qp = pc.default_params(); hp = R.params(qp)
+    cfg_kw = dict(sparse=False)
+    cfg = po.make_config(**cfg_kw)
+    hx, hy = R.seq(ref), R.seq(reads[0])
+    v = R.viterbi(hx, hy, hp, cfg)
+    f = R.forward(hx, hy, hp, cfg)
+    out = dict(cfg=cfg_kw, ref_len=50_000, ref_seed=3, read_len=10_000, read_seed=4, read_actual_len=len(reads[0]),
+               viterbi=v["result"], x_start=int(v["x_start"]), x_end=int(v["x_end"]), forward=f["result"], path_len=int(len(v["path"])))
+    with open(os.path.join(HERE, name + ".json"), "w") as fh:
+        json.dump(out, fh)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), path=rle(v["path"]))
+    print(name, out["viterbi"], out["forward"], out["x_start"], out["x_end"], out["path_len"])
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "cfg5":
+        cfg5_case()
+        sys.exit(0)
     reference_own_goldens()
+    cfg5_case()
     nullp = QuaffNullParams.load(os.path.join(HERE, "testquaffnullparams.json"))
     x, reads = pc.make_workload(ref_len=9000, n_reads=3, read_len=800, seed=41)
     synthetic_case("synth_default", pc.default_params(), x, reads, dict(kmer_threshold=14), nullp=nullp)

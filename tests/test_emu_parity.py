@@ -33,6 +33,16 @@ def test_emu_envelopes(emu, oracle, workload):
     pc.check_envelopes(emu, oracle, x, reads, api.dp_config(kmer_threshold=6), xi, yi)
 
 
+def test_emu_threshold_zero(emu, oracle, workload, monkeypatch):
+    """-kmatchn 0: only diagonals that received a hit are seeds (diagenv.cpp:33-46), on both seeding paths"""
+    x, reads, _ = workload
+    xi, yi = pc.all_pairs(len(x), len(reads))
+    pc.check_envelopes(emu, oracle, x, reads, api.dp_config(kmer_threshold=0, band_size=4), xi, yi)
+    pc.check_envelopes(emu, oracle, x, reads, api.dp_config(kmer_len=9, kmer_threshold=0, band_size=4), xi, yi)
+    monkeypatch.setenv("QG_SEED_GENERAL", "1")
+    pc.check_envelopes(emu, oracle, x, reads, api.dp_config(kmer_threshold=0, band_size=4), xi, yi)
+
+
 def test_emu_viterbi_forward(emu, oracle, workload):
     x, reads, s_or = workload
     xi, yi = pc.all_pairs(len(x), len(reads))
