@@ -104,7 +104,7 @@ class AlignScores:
 
 
 def load_library(path: Optional[str] = None) -> C.CDLL:
-    path = path or DEFAULT_LIB
+    path = path or os.environ.get("QUAFF_GPU_LIB") or DEFAULT_LIB      # QUAFF_GPU_LIB: development builds of the same library
     if not os.path.exists(path):
         raise QuaffGpuError(4, f"{path} not found: build it with `python -m quaff_b200.build` (nvcc, sm_100a); there is no CPU fallback")
     L = C.CDLL(path)

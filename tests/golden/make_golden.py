@@ -141,13 +141,13 @@ def cfg5_case(name="cfg5_full"):
     from quaff_b200.synth import random_ref, sample_reads
     ref = random_ref(50_000, 3)
     reads, starts, strands = sample_reads(ref, 1, 10_000, 4, both_strands=False)
-    qp = pc.default_params(); hp = R.params(qp)
+    qp = pc.default_params(); hp = R.params(qp); qp = R.params_as_parsed(hp, qp)
     cfg_kw = dict(sparse=False)
     cfg = po.make_config(**cfg_kw)
     hx, hy = R.seq(ref), R.seq(reads[0])
     v = R.viterbi(hx, hy, hp, cfg)
     f = R.forward(hx, hy, hp, cfg)
-    out = dict(cfg=cfg_kw, ref_len=50_000, ref_seed=3, read_len=10_000, read_seed=4, read_actual_len=len(reads[0]),
+    out = dict(cfg=cfg_kw, params=params_payload(qp), ref_len=50_000, ref_seed=3, read_len=10_000, read_seed=4, read_actual_len=len(reads[0]),
                viterbi=v["result"], x_start=int(v["x_start"]), x_end=int(v["x_end"]), forward=f["result"], path_len=int(len(v["path"])))
     with open(os.path.join(HERE, name + ".json"), "w") as fh:
         json.dump(out, fh)

@@ -107,7 +107,7 @@ def test_cfg5_full_dp_reference_vector(gpu):
     ref = random_ref(meta["ref_len"], meta["ref_seed"])
     reads, _, _ = sample_reads(ref, 1, meta["read_len"], meta["read_seed"], both_strands=False)
     assert len(reads[0]) == meta["read_actual_len"]
-    gpu.set_refs([ref]); gpu.set_reads(reads); gpu.set_params(pc.default_params())
+    gpu.set_refs([ref]); gpu.set_reads(reads); gpu.set_params(gc.params_from_payload(meta["params"]))   # as the reference parsed them
     cfg = api.dp_config(**meta["cfg"])
     v = gpu.viterbi(cfg, [0], [0])
     assert v["score"][0] == meta["viterbi"] and (int(v["x_start"][0]), int(v["x_end"][0])) == (meta["x_start"], meta["x_end"])
