@@ -32,12 +32,15 @@ sys.path.insert(0, ROOT)
 REF_LEN = 5_000_000
 READ_LEN = 8000
 READS_PER_STEP = 1536            # per GPU; ~4.3 GB of traceback pointers per step
+CFG4_WORKLOAD = ("cfg4: quaff align, synthetic 8 kb nanopore-like reads (12% error) vs 5 Mb random reference, both strands, "
+                 "-kmatch 6 -kmatchn 20 -kmatchband 64, default params, fixed null model")
 POOL_BATCHES = 2                 # distinct read batches cycled through the steps (bounds host synthesis time)
 # peak lane-instructions/s and the instructions one cell update needs in the minimal formulation
 SM_COUNT, LANES, SM_MAX_MHZ = 148, 128, 1965.0
 PEAK_LANE_INSTR = SM_COUNT * LANES * SM_MAX_MHZ * 1e6
 INSTR_PER_CU = dict(viterbi=13, forward=9, backward=25, overlap=26)
 PEAK_SMEM_ATOMIC = SM_COUNT * 32 * SM_MAX_MHZ * 1e6      # histogram increments/s upper bound
+MEASURED_SMEM_ATOMIC = SM_COUNT * 16 * SM_MAX_MHZ * 1e6  # what random full-warp shared atomics reach on this part (tools/ubench/atoms.cu)
 
 
 def measured_peaks():
@@ -111,7 +114,7 @@ def load_models():
 # ------------------------------------------------------------------------------------------------------------------
 def reference_cpu_run(n_reads: int, threads: int, ref_len: int = REF_LEN, read_len: int = READ_LEN, seed_rank: int = 0):
     """`quaff align ref.fa reads.fq -kmatchband 64 -threads T` with the reference binary built from the unmodified
-    sources (oracle/_ref/quaff).  Returns (reads/s, seconds, kind)."""
+    sources (oracle/_ref/quaff).  Returns (reads/s, seconds, kind, SAM text of the run or None)."""
     from oracle import pyoracle as po
     from quaff_b200.synth import random_ref, sample_reads
     qp, nullp = load_models()
@@ -133,8 +136,7 @@ def reference_cpu_run(n_reads: int, threads: int, ref_len: int = REF_LEN, read_l
             dt = time.time() - t0
             if res.returncode != 0:
                 raise RuntimeError("reference quaff failed: " + res.stderr[-500:])
-            n_out = sum(1 for ln in res.stdout.splitlines() if ln and not ln.startswith("@"))
-        return n_reads / dt, dt, "reference", n_out
+        return n_reads / dt, dt, "reference", res.stdout
     # no reference build here: time the C restatement (1 thread)
     O = po.Oracle()
     s = O.scores(qp)
@@ -147,37 +149,244 @@ def reference_cpu_run(n_reads: int, threads: int, ref_len: int = REF_LEN, read_l
         for x in xs:
             O.viterbi(x, y, s, cfg)
     dt = time.time() - t0
-    return n_reads / dt, dt, "port", n_reads
+    return n_reads / dt, dt, "port", None
+
+
+REFERENCE_ARM_BUDGET_S = 200.0     # the whole `--impl reference` run: one step costs ~13 s per read per core at this shape
 
 
 def run_reference_arm(args):
+    """The reference's own CPU implementation on this box's host cores.  A step = `quaff align -threads <cores>` over one
+    read per core (fewer reads would leave threads idle and understate it).  One step takes 13-16 s, so the arm runs as many
+    of the requested warm-up/timed steps as fit REFERENCE_ARM_BUDGET_S and reports the numbers it really ran."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    sample = max(2, min(cores, 32))                               # about one read per core: 13 s/read/core at this shape
-    vals = []
-    for _ in range(args.warmup + args.steps if args.ref_all_steps else 1):
-        v, dt, kind, _ = reference_cpu_run(sample, cores)
+    sample = max(2, min(cores, 32))
+    t_begin = time.time()
+    v0, dt0, kind, _ = reference_cpu_run(sample, cores, args.ref_len, args.read_len)         # first step: also the cost estimate
+    fit = max(1, int((REFERENCE_ARM_BUDGET_S - (time.time() - t_begin)) // max(dt0, 1e-3)))
+    warm = 1 if (args.warmup > 0 and fit >= 2) else 0                                        # the first run is the warm-up when a second one fits
+    steps = max(1, min(args.steps, fit if warm else fit + 1))
+    vals = [] if warm else [(v0, dt0)]
+    while len(vals) < steps:
+        v, dt, kind, _ = reference_cpu_run(sample, cores, args.ref_len, args.read_len)
         vals.append((v, dt))
-    v = float(np.mean([a for a, _ in vals])); dt = float(np.mean([b for _, b in vals]))
+    dt = float(np.mean([b for _, b in vals])); v = sample / dt
     line = {
-        "impl": "reference", "metric": "align_reads_per_sec", "value": v, "unit": "reads/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "cfg4: quaff align, 8 kb reads vs 5 Mb reference, both strands, -kmatch 6 -kmatchn 20 -kmatchband 64",
-                   "reads_per_step": sample, "note": "bounded sample of the same workload; reference CPU implementation, all host threads"},
-        "cpu_baseline": {"value": v, "unit": "reads/s", "cores": cores, "kind": kind, "sample": f"{sample} reads x 8 kb vs 5 Mb, both strands, -threads {cores}"},
+        "impl": "reference", "metric": "align_reads_per_sec", "value": v, "unit": "reads/s", "n_gpus": args.gpus, "steps": len(vals),
+        "warmup": warm, "requested_steps": args.steps, "requested_warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": CFG4_WORKLOAD, "reads_per_step_per_gpu": sample, "ref_len": args.ref_len, "read_len": args.read_len,
+                   "note": "reference CPU implementation (oracle/_ref/quaff align -threads <cores>, unmodified sources, -O3); a step is one read per "
+                           "host core of the same workload; steps/warmup are what was run inside the arm's %d s budget" % int(REFERENCE_ARM_BUDGET_S)},
+        "cpu_baseline": {"value": v, "unit": "reads/s", "cores": cores, "kind": kind,
+                         "sample": f"{sample} reads x {args.read_len} b vs {args.ref_len} b, both strands, -threads {cores}, {len(vals)} timed run(s)"},
         "e2e": {"value": v, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
 
 
 # ------------------------------------------------------------------------------------------------------------------
+def _dist_setup():
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device: there is no CPU path"
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    return torch, dist, rank, world, local, barrier
+
+
+def run_cfg5(args):
+    """BASELINE config 5: `quaff align -kmatchoff` (full, unbanded DP) on synthetic 10 kb reads against a 50 kb reference,
+    both strands -- the tiled wavefront of qg_tile.cuh.  A step = `--reads-per-step` reads (default 16) of the 2 000."""
+    from quaff_b200 import api
+    from quaff_b200.seqs import add_revcomps
+    from quaff_b200.synth import random_ref, sample_reads
+    torch, dist, rank, world, local, barrier = _dist_setup()
+    B = args.reads_per_step if args.reads_per_step != READS_PER_STEP else 16
+    ref = random_ref(50_000, 3)                                                     # SURVEY 8d: reference seed 3, reads seed 4
+    x = add_revcomps([ref])
+    batches = [sample_reads(ref, B, 10_000, 4 + 1000 * rank + b, name_prefix=f"r{rank}b{b}_")[0] for b in range(POOL_BATCHES)]
+    qp, nullp = load_models()
+    G = api.QuaffGPU(device=local)
+    G.set_refs(x); G.set_params(qp)
+    cfg = api.dp_config(sparse=False)
+    null_ll = [np.array([api.null_loglike(nullp, r, G.L) for r in b]) for b in batches]
+    flat = [api._flatten(b, True) for b in batches]
+
+    def step(i):
+        tok, qual, off = flat[i % POOL_BATCHES]
+        G.set_seqs_raw(api.QG_READS, tok, qual, off)
+        return G.align_reads(cfg, null_ll[i % POOL_BATCHES], split_paths=False)
+    for i in range(args.warmup):
+        step(i)
+    sampler = ClockSampler(local); sampler.start()
+    G.stats(reset=True)
+    barrier(); t0 = time.perf_counter()
+    for i in range(args.steps):
+        r = step(args.warmup + i)
+    barrier(); t1 = time.perf_counter()
+    clocks = sampler.stop()
+    st = G.stats()
+    times = torch.tensor([t1 - t0], dtype=torch.float64, device="cuda")
+    sums = torch.tensor([float(st["cell_updates"]), st["ms_viterbi"], float(st["kernel_launches"])], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX); dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+    dt = float(times[0])
+    if rank == 0:
+        cu = float(sums[0]); ms_fill = float(sums[1]) / world
+        gcups_fill = cu / world / (ms_fill / 1e3) / 1e9
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            from oracle import pyoracle as po
+            if os.path.exists(po.REF_QUAFF):
+                with tempfile.TemporaryDirectory() as td:
+                    fa, fq, pj, nj = (os.path.join(td, n) for n in ("ref.fa", "reads.fq", "params.json", "null.json"))
+                    open(fa, "w").write(f">{ref.name}\n{ref.seq}\n")
+                    r0 = batches[0][0]
+                    open(fq, "w").write(f"@{r0.name}\n{r0.seq}\n+\n{r0.qual}\n")
+                    open(pj, "w").write(qp.to_json()); open(nj, "w").write(nullp.to_json())
+                    tc = time.time()
+                    res = subprocess.run([po.REF_QUAFF, "align", fa, fq, "-params", pj, "-null", nj, "-kmatchoff", "-format", "sam", "-threads", "2"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+                    secs = time.time() - tc
+                if res.returncode == 0:
+                    from quaff_b200 import sam
+                    G.set_reads([r0])
+                    g1 = G.align_reads(cfg, null_ll[0][:1], split_paths=False)
+                    checked = sam.compare_batch(res.stdout, [r0], ref.name, len(ref), g1)
+                    cpu = {"value": 1.0 / secs, "unit": "reads/s", "cores": 2, "kind": "reference", "parity_checked": checked,
+                           "sample": f"1 read x 10 kb vs 50 kb, both strands, quaff align -kmatchoff -threads 2 ({secs:.1f} s; 12 GB per strand)"}
+        line = {
+            "metric": "align_reads_per_sec", "value": B * args.steps * world / dt, "unit": "reads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "cfg5: quaff align -kmatchoff (full DP), synthetic 10 kb reads vs 50 kb reference, both strands, default params",
+                       "reads_per_step_per_gpu": B, "ref_len": 50_000, "read_len": 10_000,
+                       "l2": "every step writes and re-reads its own pointer tiles (4 bit per cell, ~%.1f GB per step), far larger than L2" % (cu / world / args.steps / 2 / 1e9)},
+            "e2e": {"value": B * args.steps * world / dt, "unit": "reads/s", "h2d_bytes_per_step": int(sum(a.nbytes for a in flat[0] if a is not None)),
+                    "d2h_bytes_per_step": int(r["paths"].nbytes + 8 * 4 * B), "note": "this workload is timed through the host-buffer call only"},
+            "gpu_launches": int(float(sums[2]) / world), "clocks": clocks,
+            "gcups": {"viterbi_fill_wall": cu / dt / 1e9, "viterbi_fill_kernels": gcups_fill, "cell_updates_per_read": cu / (B * args.steps * world)},
+            "roofline": {"kernel": "qg_tile_kernel<0>", "bound": "lane_instr", "achieved": gcups_fill, "peak": PEAK_LANE_INSTR / INSTR_PER_CU["viterbi"] / 1e9,
+                         "unit": "GCUPS", "frac": gcups_fill * 1e9 / (PEAK_LANE_INSTR / INSTR_PER_CU["viterbi"]), "traffic": None},
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    G.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_train(args):
+    """One EM E-step per step (seam C, QuaffTrainer::getCounts, qmodel.cpp:2005-2032) over this rank's shard of cfg4-shaped
+    reads: Forward of every read x strand, Backward + counts of the pairs that pass the gate, then ONE all-reduce of the
+    QuaffParamCounts (+ log-likelihood) over the ranks -- NCCL over NVLink.  Before timing, the collective is checked: every rank
+    runs a few reads, the reduced counts must equal what rank 0 gets from all of those reads alone (1e-9 relative)."""
+    from quaff_b200 import api
+    from quaff_b200.dist import allreduce_counts
+    torch, dist, rank, world, local, barrier = _dist_setup()
+    B = args.reads_per_step if args.reads_per_step != READS_PER_STEP else 256
+    x, batches = make_workload(rank, POOL_BATCHES, B, args.ref_len, args.read_len)
+    qp, nullp = load_models()
+    G = api.QuaffGPU(device=local)
+    G.set_refs(x); G.set_params(qp)
+    cfg = api.dp_config(kmer_threshold=20, band_size=64, kmer_len=6)
+    null_ll = [np.array([api.null_loglike(nullp, r, G.L) for r in b]) for b in batches]
+
+    # ---- the collective, checked on a small global read list every rank can build (seed 9) --------------------------------
+    allreduce_checked = None
+    if world > 1:
+        from quaff_b200.synth import sample_reads
+        per = 3
+        greads, _, _ = sample_reads(x[0], per * world, args.read_len, 9, name_prefix="g")
+        gnull = np.array([api.null_loglike(nullp, r, G.L) for r in greads])
+        lo, hi = rank * per, (rank + 1) * per
+        G.set_reads(greads[lo:hi])
+        mine = G.estep(cfg, True, gnull[lo:hi])
+        red_counts, red_ll = allreduce_counts(mine["counts"], mine["loglike"])
+        if rank == 0:
+            G.set_reads(greads)
+            alone = G.estep(cfg, True, gnull)
+            scale = max(1.0, float(np.abs(alone["counts"]).max()))
+            err = float(np.max(np.abs(red_counts - alone["counts"]) / (np.abs(alone["counts"]) + 1e-9 * scale)))
+            assert err <= 1e-9 and abs(red_ll - alone["loglike"]) <= 1e-9 * abs(alone["loglike"]), (err, red_ll, alone["loglike"])
+            allreduce_checked = {"reads": per * world, "max_rel_err": err, "loglike_abs_err": abs(red_ll - alone["loglike"])}
+
+    ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
+    ar_ms = []
+
+    def step(i, timed=False):
+        b = i % POOL_BATCHES
+        G.set_reads(batches[b])
+        r = G.estep(cfg, True, null_ll[b])
+        ev0.record()
+        counts, ll = allreduce_counts(r["counts"], r["loglike"])
+        ev1.record(); ev1.synchronize()
+        if timed:
+            ar_ms.append(ev0.elapsed_time(ev1))
+        return counts, ll
+    for i in range(args.warmup):
+        step(i)
+    sampler = ClockSampler(local); sampler.start()
+    G.stats(reset=True)
+    barrier(); t0 = time.perf_counter()
+    for i in range(args.steps):
+        counts, ll = step(args.warmup + i, True)
+    barrier(); t1 = time.perf_counter()
+    clocks = sampler.stop()
+    st = G.stats()
+    times = torch.tensor([t1 - t0, float(np.mean(ar_ms))], dtype=torch.float64, device="cuda")
+    # Forward visits every envelope cell once; the Backward pass visits the gated pairs' cells again (cell_updates counts both)
+    sums = torch.tensor([float(st["cell_updates"]), st["ms_forward"], st["ms_backward"], st["ms_seed"], float(st["kernel_launches"]), float(st["fwd_store_bytes"])],
+                        dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX); dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+    dt = float(times[0])
+    if rank == 0:
+        cu = float(sums[0]); ms_f = float(sums[1]) / world; ms_b = float(sums[2]) / world; ms_s = float(sums[3]) / world
+        h2d = int(sum(a.nbytes for a in api._flatten(batches[0], True) if a is not None))
+        line = {
+            "metric": "train_estep_reads_per_sec", "value": B * args.steps * world / dt, "unit": "reads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "train E-step over cfg4's reads: 8 kb reads vs 5 Mb reference, both strands, -kmatch 6 -kmatchn 20 -kmatchband 64, default params, "
+                                   "fixed null model; Forward of every pair, Backward + counts of the gated pairs, one counts all-reduce per step",
+                       "reads_per_step_per_gpu": B, "ref_len": args.ref_len, "read_len": args.read_len,
+                       "collective": "all-reduce (sum) of %d doubles per step, %s" % (len(counts) + 1, "NCCL" if world > 1 else "single rank: no-op"),
+                       "l2": "every step streams its own Forward checkpoints / row parameters, larger than L2; 2 read batches alternate"},
+            "e2e": {"value": B * args.steps * world / dt, "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(8 * (len(counts) + 1 + B)),
+                    "note": "every step uploads its reads from host buffers and returns counts + per-read log-likelihoods to the host"},
+            "gpu_launches": int(float(sums[4]) / world), "clocks": clocks,
+            "gcups": {"forward_backward_wall": cu / dt / 1e9, "cells_per_step_per_gpu": cu / world / args.steps,
+                      "forward_backward_kernels": cu / world / ((ms_f + ms_b) / 1e3) / 1e9,
+                      "ms_forward_per_step": ms_f / args.steps, "ms_backward_per_step": ms_b / args.steps, "ms_seed_per_step": ms_s / args.steps},
+            "allreduce": {"ms_per_step_max_over_ranks": float(times[1]), "doubles": len(counts) + 1, "checked": allreduce_checked},
+            "roofline": {"kernel": "qg_forward/backward", "bound": "lane_instr", "achieved": cu / world / ((ms_f + ms_b) / 1e3) / 1e9,
+                         "peak": PEAK_LANE_INSTR / ((INSTR_PER_CU["forward"] + INSTR_PER_CU["backward"]) / 2) / 1e9, "unit": "GCUPS",
+                         "frac": cu / world / ((ms_f + ms_b) / 1e3) / (PEAK_LANE_INSTR / ((INSTR_PER_CU["forward"] + INSTR_PER_CU["backward"]) / 2)),
+                         "traffic": None, "fwd_store_bytes_per_step": float(sums[5]) / world / args.steps},
+            "loglike": ll,
+        }
+        print(json.dumps(line), flush=True)
+    G.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--steps", type=int, default=48, help="timed steps (default: ~4 s per arm at ~80 ms/step)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="quaff_b200")
     ap.add_argument("--reads-per-step", type=int, default=READS_PER_STEP)
@@ -185,7 +394,9 @@ def main():
     ap.add_argument("--read-len", type=int, default=READ_LEN)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the Forward/Backward side measurement")
-    ap.add_argument("--ref-all-steps", action="store_true")
+    ap.add_argument("--workload", default="cfg4", choices=["cfg4", "cfg5", "train"],
+                    help="cfg4: the headline align benchmark (default, the contract line); cfg5: -kmatchoff full DP, 10 kb reads vs 50 kb; "
+                         "train: one E-step (Forward + Backward + counts) per step over cfg4's reads with the counts all-reduce")
     ap.add_argument("--contexts", type=int, default=4, help="contexts (host thread + stream each) per GPU")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl != "reference":
@@ -193,6 +404,10 @@ def main():
     if args.impl == "reference":
         run_reference_arm(args)
         return
+    if args.workload == "cfg5":
+        return run_cfg5(args)
+    if args.workload == "train":
+        return run_train(args)
 
     import torch
     import torch.distributed as dist
@@ -247,8 +462,12 @@ def main():
     barrier(); t0 = time.perf_counter()
     outs = P.align_batches(cfg, [((args.warmup + i) % POOL_BATCHES, null_ll[(args.warmup + i) % POOL_BATCHES]) for i in range(args.steps)])
     barrier(); t1 = time.perf_counter()
-    out = outs[-1]
     assert len(outs) == args.steps
+    # a batch-0 result of the timed region (or one more untimed pass when no timed step used batch 0): diffed against the
+    # reference CLI's SAM for its first reads further down
+    b0 = [i for i in range(args.steps) if (args.warmup + i) % POOL_BATCHES == 0]
+    parity_result = outs[b0[-1]] if b0 else P.align_batch(cfg, 0, null_ll[0])
+    parity_from = "timed region" if b0 else "extra untimed pass"
     st_timed = pool_stats()
     dt = t1 - t0
     # ---- e2e arm: host buffers in, host results out, every step ---------------------------------------------------
@@ -334,9 +553,10 @@ def main():
         seed_bytes = 2.0 * (args.ref_len * 2) * iso_reads
         vit_bytes = float(sums[6]) / world
         # DRAM traffic of the dominant kernel per launch, from the committed ncu --set full capture of this same workload
-        traffic = None
+        traffic = None; traffic_file = None
         try:
-            tj = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01g_traffic.json")))
+            traffic_file = "r02_traffic.json" if os.path.exists(os.path.join(ROOT, "profiles", "r02_traffic.json")) else "r01g_traffic.json"
+            tj = json.load(open(os.path.join(ROOT, "profiles", traffic_file)))
             w = tj["workload"]
             if (w["ref_len"], w["read_len"]) == (args.ref_len, args.read_len):
                 k = tj["qg_seed_kernel" if seed_dom else "qg_vit_kernel<3>"]
@@ -346,55 +566,60 @@ def main():
             traffic = None
         seed_gbps = seed_bytes / (ms_seed / 1e3) / 1e9
         vit_gbps = vit_bytes / (ms_vit / 1e3) / 1e9
-        compute = {
-            "kernel": "qg_seed_kernel" if seed_dom else "qg_vit_kernel<R>",
-            "bound": "smem_atomic" if seed_dom else "fp64_issue",
-            "achieved": seed_hps / 1e9 if seed_dom else vit_cups / 1e9,
-            "peak": PEAK_SMEM_ATOMIC / 1e9 if seed_dom else PEAK_LANE_INSTR / INSTR_PER_CU["viterbi"] / 1e9,
-            "unit": "Ghit/s" if seed_dom else "GCUPS",
-            "frac": (seed_hps / PEAK_SMEM_ATOMIC) if seed_dom else vit_cups / (PEAK_LANE_INSTR / INSTR_PER_CU["viterbi"]),
-            "definition": "SURVEY.md 8d / DESIGN.md 4.1: the dominant kernel is bound by shared-memory atomics / instruction issue, not by HBM or tensor "
-                          "cores; peaks are the shared-memory atomic issue rate (148 SM x 32 lanes x 1965 MHz) and 148 x 128 x 1965 MHz "
-                          "lane-instructions/s over 13 instr per cell update",
+        seed_view = {
+            "kernel": "qg_seed_kernel", "bound": "smem_atomic", "achieved": seed_hps / 1e9, "peak": PEAK_SMEM_ATOMIC / 1e9, "unit": "Ghit/s",
+            "frac": seed_hps / PEAK_SMEM_ATOMIC,
+            "measured_peak": MEASURED_SMEM_ATOMIC / 1e9, "frac_of_measured_peak": seed_hps / MEASURED_SMEM_ATOMIC,
+            "definition": "SURVEY.md 8d / DESIGN.md 4.1: one shared-memory atomic per k-mer hit; peak = 148 SM x 32 lanes x 1965 MHz.  measured_peak = the "
+                          "rate tools/ubench/atoms.cu reaches with all 32 lanes active on random counters (16 per cycle per SM; bank conflicts of a "
+                          "random scatter are part of the problem)",
         }
-        roofline = {
-            "kernel": compute["kernel"],
-            "bound": "hbm",
-            "achieved": seed_gbps if seed_dom else vit_gbps,
-            "peak": hbm_peak, "unit": "GB/s",
-            "frac": (seed_gbps if seed_dom else vit_gbps) / hbm_peak,
+        vit_view = {
+            "kernel": "qg_vit_kernel<R>", "bound": "lane_instr", "achieved": vit_cups / 1e9, "peak": PEAK_LANE_INSTR / INSTR_PER_CU["viterbi"] / 1e9,
+            "unit": "GCUPS", "frac": vit_cups / (PEAK_LANE_INSTR / INSTR_PER_CU["viterbi"]),
+            "definition": "SURVEY.md 8d: 148 SM x 128 lanes x 1965 MHz lane-instructions/s over 13 instructions per cell update (FP32-minimal form; the "
+                          "kernel computes in FP64 for bit-exact paths, whose issue rate is half: frac_fp64 = 2 x frac)",
+        }
+        roofline = dict(seed_view if seed_dom else vit_view)
+        roofline.update({
             "traffic": traffic,
-            "traffic_source": "profiles/r01g_traffic.json (ncu --set full capture of this workload, scaled to this run's reads per launch)",
-            "peak_source": peak_src,
-            "algorithmic_bytes": "seeding: 2 B k-mer code per reference position per pair-strand (DESIGN.md 4.1); Viterbi: 4 B of pointers per lane and macro-step",
-            "note": "the HBM view the contract asks for; DRAM traffic is far below the algorithmic bytes because the code stream is served by L2. "
-                    "The kernel's real limiter is in `compute`",
-            "compute": compute,
-            "hbm": {"seed_GBps": seed_gbps, "viterbi_trace_GBps": vit_gbps, "peak_GBps": hbm_peak, "peak_source": peak_src},
-            "all": {"seed_ghits_s": seed_hps / 1e9, "seed_frac_of_smem_atomic_peak": seed_hps / PEAK_SMEM_ATOMIC,
-                    "viterbi_gcups": vit_cups / 1e9, "viterbi_frac_of_fp32_roofline": vit_cups / (PEAK_LANE_INSTR / INSTR_PER_CU["viterbi"]),
-                    "viterbi_frac_of_fp64_roofline": vit_cups / (PEAK_LANE_INSTR / 2 / INSTR_PER_CU["viterbi"]),
+            "traffic_source": "profiles/%s (ncu --set full capture of this workload, scaled to this run's reads per launch)" % traffic_file,
+            "algorithmic_bytes": seed_bytes / n_iso if seed_dom else vit_bytes / n_iso,
+            "algorithmic_bytes_note": "per launch of the isolated pass.  seeding: 2 B k-mer code per reference position per read-strand (DESIGN.md 4.1), served "
+                                      "by L2 -- DRAM traffic is ~0.2% of it, the kernel is not HBM-bound; Viterbi: the traceback pointers it writes",
+            "hbm": {"seed_GBps": seed_gbps, "viterbi_trace_GBps": vit_gbps, "peak_GBps": hbm_peak, "peak_source": peak_src,
+                    "seed_frac": seed_gbps / hbm_peak, "viterbi_frac": vit_gbps / hbm_peak},
+            "all": {"seed": seed_view, "viterbi": vit_view,
                     "isolated_pass": {"reads": iso_reads, "ms_seed": ms_seed, "ms_viterbi_fill": ms_vit, "ms_traceback": ms_tb,
                                       "note": "one context alone after the timed regions; kernel times by CUDA events on its stream"}},
-        }
+        })
         if train:
             roofline["all"]["forward_gcups"] = train["forward_gcups"]; roofline["all"]["backward_gcups"] = train["backward_gcups"]
         cpu = None
+        parity_checked = 0; parity_note = "cpu_baseline leg not run"
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             sample = max(2, min(cores, 32))
+            sam_text = None
             try:
-                v, secs, kind, _ = reference_cpu_run(sample, cores, args.ref_len, args.read_len)
+                v, secs, kind, sam_text = reference_cpu_run(sample, cores, args.ref_len, args.read_len)
                 cpu = {"value": v, "unit": "reads/s", "cores": cores, "kind": kind,
                        "sample": f"{sample} reads x {args.read_len} b vs {args.ref_len} b, both strands, quaff align -threads {cores} ({secs:.1f} s)"}
             except Exception as e:                                    # the baseline is reported, never required
                 cpu = {"value": None, "unit": "reads/s", "cores": cores, "kind": "unavailable", "sample": str(e)[:200]}
+            if sam_text is not None:
+                # the same reads went through the GPU batch: best strand, POS, CIGAR and AS:i: must be the reference's
+                # (Alignment::writeSam, qmodel.cpp:611-622).  A difference is fatal: a fast wrong answer is not a result.
+                from quaff_b200 import sam
+                parity_checked = sam.compare_batch(sam_text, batches[0][:sample], x[0].name, len(x[0]), parity_result)
+                parity_note = f"first {sample} reads of batch 0 ({parity_from}) vs the SAM of oracle/_ref/quaff: strand, POS, CIGAR, AS:i identical"
+            else:
+                parity_note = "no reference build on this box (oracle port timed): SAM comparison skipped"
         line = {
             "metric": "align_reads_per_sec", "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "cfg4: quaff align, synthetic 8 kb nanopore-like reads (12% error) vs 5 Mb random reference, both strands, "
-                                   "-kmatch 6 -kmatchn 20 -kmatchband 64, default params, fixed null model",
+            "config": {"workload": CFG4_WORKLOAD,
                        "reads_per_step_per_gpu": B, "ref_len": args.ref_len, "read_len": args.read_len, "contexts_per_gpu": args.contexts,
                        "sharding": "reads over ranks, reference replicated, no collective on the align path",
                        "pipelining": "each context works through its share of the K timed steps without a per-step join; every step's results reach the host",
@@ -406,6 +631,7 @@ def main():
             "gcups": {"viterbi_fill": vit_cups / 1e9, "cell_updates_per_read": cu_rank / iso_reads, "kmer_hits_per_read": hits_rank / iso_reads},
             "roofline": roofline,
             "cpu_baseline": cpu,
+            "parity_checked": parity_checked, "parity_note": parity_note,
             "train": train,
         }
         print(json.dumps(line), flush=True)
