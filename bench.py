@@ -112,14 +112,14 @@ def load_models():
 
 
 # ------------------------------------------------------------------------------------------------------------------
-def reference_cpu_run(n_reads: int, threads: int, ref_len: int = REF_LEN, read_len: int = READ_LEN, seed_rank: int = 0):
+def reference_cpu_run(n_reads: int, threads: int, ref_len: int = REF_LEN, read_len: int = READ_LEN, seed_rank: int = 0, name_prefix: str = "r0b0_"):
     """`quaff align ref.fa reads.fq -kmatchband 64 -threads T` with the reference binary built from the unmodified
     sources (oracle/_ref/quaff).  Returns (reads/s, seconds, kind, SAM text of the run or None)."""
     from oracle import pyoracle as po
     from quaff_b200.synth import random_ref, sample_reads
     qp, nullp = load_models()
     ref = random_ref(ref_len, 1)
-    reads, _, _ = sample_reads(ref, n_reads, read_len, 2 + 1000 * seed_rank, name_prefix="r")
+    reads, _, _ = sample_reads(ref, n_reads, read_len, 2 + 1000 * seed_rank, name_prefix=name_prefix)   # = the first reads of rank 0's batch 0
     if os.path.exists(po.REF_QUAFF):
         with tempfile.TemporaryDirectory() as td:
             fa, fq = os.path.join(td, "ref.fa"), os.path.join(td, "reads.fq")

@@ -57,6 +57,9 @@ struct qg_seqset {
   // k-mer codes (uint16 per position, 0xFFFF = no k-mer starts here), cached for one k
   int codes_k = 0;
   qg_dbuf d_codes;
+  // tiles of QG_TILE_POS positions sorted by k-mer code (uint32 per position: code << 16 | position in tile), for one k
+  int sorted_k = 0;
+  qg_dbuf d_sorted;
   uint32_t max_len = 0;
   uint32_t len (size_t i) const { return (uint32_t) (off[i + 1] - off[i]); }
 };

@@ -265,6 +265,264 @@ qg_seed_kernel (const qg_seed_item* __restrict__ items, const qg_pair_desc* __re
   if (lane == 0 && my_hits64) atomicAdd (hit_counter, my_hits64);
 }
 
+// ---- the tile-sorted histogram kernel (k = 5, 6; reads up to 16 380 + k bases) ------------------------------------
+// The reference side is static, so it is prepared once per sequence set: every tile of QG_TILE_POS consecutive
+// positions is sorted by k-mer code (qg_sort_tiles_kernel; entry = code << 16 | position in the tile, 4 B/position).
+// Lanes of a warp then look up neighbouring codes -- the header loads become near-broadcasts instead of 32 random
+// 8-byte reads -- and walk buckets of equal length.  The bucket header holds the first FOUR entries (4 x 14 bit + 8-bit
+// length), issued as four predicated shared-memory increments without a branch; longer buckets (4.8 % of the codes at
+// 8 kb) continue from the full bucket array under a warp vote.  What bounds the kernel is the shared-memory pipe
+// (wavefronts: bank conflicts of a random scatter), measured in tools/ubench/seedloop2.cu; DESIGN.md 4.1.
+// One CTA of QG_TSEED_THREADS threads per SM (the ring alone is 128 KB) at <= 40 registers, which leaves register file
+// and warp slots for the DP kernels of the other contexts to run on the same SMs.
+#ifdef QG_EMU                        /* CPU-thread shim of the tests: small tiles, so that short inputs cross tile and item boundaries */
+#define QG_TILE_POS 1024
+#define QG_TSEED_RING 4096u
+#define QG_TSEED_THREADS 128
+#else
+#define QG_TILE_POS 16384
+#define QG_TSEED_RING 32768u
+#define QG_TSEED_THREADS 1024
+#endif
+#define QG_TSEED_ESTEP (QG_TSEED_THREADS * 8)      // diagonals one pass of the emit scan covers
+
+struct qg_tile_job { uint64_t off; uint32_t len; uint32_t pad_; };   // one tile: positions [off, off + len) of the flat code array
+
+__global__ void __launch_bounds__ (256)
+qg_sort_tiles_kernel (const qg_tile_job* __restrict__ jobs, const uint16_t* __restrict__ codes, uint32_t nk, uint32_t* __restrict__ sorted) {
+  __shared__ uint32_t cnt[4096 + 1];
+  __shared__ uint32_t s_warp_tot[8];
+  const qg_tile_job jb = jobs[blockIdx.x];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  for (uint32_t c = tid; c <= nk; c += 256) cnt[c] = 0;
+  __syncthreads ();
+  for (uint32_t p = tid; p < jb.len; p += 256) { uint32_t c = codes[jb.off + p]; if (c > nk) c = nk; atomicAdd (&cnt[c], 1u); }
+  __syncthreads ();
+  const uint32_t per = (nk + 1 + 255) / 256;
+  const uint32_t cb = tid * per, ce = (cb + per < nk + 1) ? cb + per : nk + 1;
+  uint32_t sum = 0;
+  for (uint32_t c = cb; c < ce; ++c) sum += cnt[c];
+  uint32_t incl = sum;
+  for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync (QG_FULL_MASK, incl, o); if (lane >= o) incl += v; }
+  if (lane == 31) s_warp_tot[wid] = incl;
+  __syncthreads ();
+  uint32_t run = incl - sum;
+  for (int w = 0; w < wid; ++w) run += s_warp_tot[w];
+  for (uint32_t c = cb; c < ce; ++c) { const uint32_t v = cnt[c]; cnt[c] = run; run += v; }
+  __syncthreads ();
+  for (uint32_t p = tid; p < jb.len; p += 256) {
+    const uint32_t c16 = codes[jb.off + p];
+    const uint32_t slot = atomicAdd (&cnt[c16 > nk ? nk : c16], 1u);
+    sorted[jb.off + slot] = (c16 << 16) | p;
+  }
+}
+
+#ifdef QG_EMU
+#define QG_RED_IF(addr, pred) do { if (pred) atomicAdd ((addr), 1u); } while (0)
+#else
+#define QG_RED_IF(addr, pred) asm volatile ("{ .reg .pred q; setp.ne.u32 q, %1, 0; @q red.shared.add.u32 [%0], 1; }" \
+    :: "r" ((uint32_t) __cvta_generic_to_shared (addr)), "r" ((uint32_t) (pred)) : "memory")
+#endif
+
+// shared memory: cnt[QG_TSEED_RING] u32 | hdr[nk + 1] uint2 | bstart[nk + 2] u16 | bpos[ymax + 2] u16 | seedmask[ESTEP/32 + 2] u32
+//   hdr[code]  = first four bucket entries (14 bit each) | min(length, 255) << 56; hdr[nk] = empty (positions without a k-mer)
+//   bpos       = span - j for every k-mer start j of the read, bucket by bucket; bstart[code] = first entry of the bucket
+//   ring slot of diagonal d = (d + span + off) & (ring - 1); off in 0..3 makes the item's first diagonal 16-byte aligned
+template<bool COUNTS>
+__global__ void __launch_bounds__ (QG_TSEED_THREADS, 1)
+qg_seed_tile_kernel (const qg_seed_item* __restrict__ items, const qg_pair_desc* __restrict__ pairs,
+                     const uint32_t* __restrict__ xsorted, const uint16_t* __restrict__ ycodes,
+                     int k, int threshold, int half_band, uint32_t ymax, uint32_t run_cap,
+                     int2* __restrict__ item_runs, uint32_t* __restrict__ item_nruns, unsigned long long* __restrict__ hit_counter,
+                     uint32_t* __restrict__ overflow_flag, uint32_t* __restrict__ counts_out) {
+  QG_DYN_SMEM (smem);
+  constexpr int T = QG_TSEED_THREADS;
+  const uint32_t nk = 1u << (2 * k);
+  const uint32_t ring = QG_TSEED_RING, mask = ring - 1;
+  uint32_t* cnt = (uint32_t*) smem;
+  uint2* hdr = (uint2*) (cnt + ring);
+  uint16_t* bstart = (uint16_t*) (hdr + nk + 1);
+  uint16_t* bpos = bstart + ((nk + 2 + 3) & ~3u);
+  uint32_t* seedmask = (uint32_t*) (bpos + ((ymax + 2 + 1) & ~1u));
+  __shared__ uint32_t s_warp_tot[T / 32];
+  __shared__ int s_open_lo, s_open_hi, s_have_open;
+  __shared__ uint32_t s_nruns;
+
+  const qg_seed_item it = items[blockIdx.x];
+  const qg_pair_desc pd = pairs[it.pair];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int xlen = (int) pd.xlen, ylen = (int) pd.ylen;
+  const int nyk = ylen - k + 1, span = ylen - k;
+  const uint16_t* yc = ycodes + pd.yoff;
+
+  // -- 1. bucket index of the read (counting sort of its k-mer starts by code)
+  for (uint32_t c = tid; c < ring; c += T) cnt[c] = 0;
+  if (tid == 0) { s_have_open = 0; s_nruns = 0; s_open_lo = 0; s_open_hi = 0; }
+  __syncthreads ();
+  for (int j = tid; j < nyk; j += T) atomicAdd (&cnt[yc[j]], 1u);
+  __syncthreads ();
+  const uint32_t per = (nk + T - 1) / T;
+  const uint32_t cb = tid * per < nk ? tid * per : nk, ce = (cb + per < nk) ? cb + per : nk;
+  {
+    uint32_t sum = 0;
+    for (uint32_t c = cb; c < ce; ++c) sum += cnt[c];
+    uint32_t incl = sum;
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync (QG_FULL_MASK, incl, o); if (lane >= o) incl += v; }
+    if (lane == 31) s_warp_tot[wid] = incl;
+    __syncthreads ();
+    uint32_t run = incl - sum;
+    for (int w = 0; w < wid; ++w) run += s_warp_tot[w];
+    for (uint32_t c = cb; c < ce; ++c) { const uint32_t v = cnt[c]; bstart[c] = (uint16_t) run; cnt[c] = run; run += v; }
+    if (tid == 0) { bstart[nk] = (uint16_t) nyk; bstart[nk + 1] = (uint16_t) nyk; }
+  }
+  __syncthreads ();
+  for (int j = tid; j < nyk; j += T) { const uint32_t slot = atomicAdd (&cnt[yc[j]], 1u); bpos[slot] = (uint16_t) (span - j); }
+  __syncthreads ();
+  for (uint32_t c = cb; c < ce; ++c) {
+    const uint32_t st = bstart[c], len = (uint32_t) bstart[c + 1] - st;
+    unsigned long long v = (unsigned long long) (len < 255u ? len : 255u) << 56;
+    for (uint32_t t = 0; t < 4 && t < len; ++t) v |= (unsigned long long) bpos[st + t] << (14 * t);
+    hdr[c] = make_uint2 ((uint32_t) v, (uint32_t) (v >> 32));
+  }
+  if (tid == 0) hdr[nk] = make_uint2 (0u, 0u);
+  for (uint32_t c = tid; c < ring; c += T) cnt[c] = 0;
+  __syncthreads ();
+
+  // -- 2. tile by tile along the reference
+  const int d_begin = it.d_begin, d_end = it.d_end;
+  const int i_begin = d_begin > 0 ? d_begin : 0;
+  int i_last = d_end - 1 + span;                          // inclusive
+  if (i_last > xlen - k) i_last = xlen - k;
+  const int min_diag = 1 - ylen, max_diag = xlen - 1;
+  const uint32_t dlen = (uint32_t) (d_end - d_begin);
+  const int off = (4 - ((d_begin + span) & 3)) & 3;
+  const int spo = span + off;                             // (d_begin + spo) is a multiple of 4
+  int emit_lo = d_begin;
+  uint32_t my_hits = 0;                                   // per thread: at most (chunk + span) / T positions x bucket length
+
+  for (int tile = i_begin / QG_TILE_POS; tile <= i_last / QG_TILE_POS; ++tile) {
+    const int tb = tile * QG_TILE_POS;
+    const int tn = (xlen - tb < QG_TILE_POS) ? xlen - tb : QG_TILE_POS;
+    const bool interior = tb >= d_begin + span && tb + tn <= d_end;      // every hit of every position belongs to the item
+    const uint32_t* xs = xsorted + pd.xoff + (uint64_t) tb;
+    const uint32_t tbo = (uint32_t) (tb + off);
+    const uint32_t ibase = (uint32_t) (tb - span - d_begin);             // d - d_begin = ibase + position + entry
+    for (int e0 = 0; e0 < tn; e0 += 4 * T) {
+      uint32_t ent[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) { const int e = e0 + r * T + tid; ent[r] = e < tn ? xs[e] : 0xFFFFFFFFu; }
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        uint32_t code = ent[r] >> 16;
+        code = code < nk ? code : nk;
+        const uint32_t pos = ent[r] & 0xFFFFu;
+        const uint32_t io = tbo + pos;
+        const uint2 h = hdr[code];
+        const uint32_t len = h.y >> 24;
+        const uint32_t e_0 = h.x & 0x3FFFu, e_1 = (h.x >> 14) & 0x3FFFu, e_2 = ((h.x >> 28) | (h.y << 4)) & 0x3FFFu, e_3 = (h.y >> 10) & 0x3FFFu;
+        if (interior) {
+          QG_RED_IF (cnt + ((io + e_0) & mask), len > 0);
+          QG_RED_IF (cnt + ((io + e_1) & mask), len > 1);
+          QG_RED_IF (cnt + ((io + e_2) & mask), len > 2);
+          QG_RED_IF (cnt + ((io + e_3) & mask), len > 3);
+          my_hits += len < 4 ? len : 4;
+          if (__any_sync (QG_FULL_MASK, len > 4)) {
+            uint32_t st = (uint32_t) bstart[code] + 4, en = len > 4 ? (uint32_t) bstart[code + 1] : 0u;
+            while (__any_sync (QG_FULL_MASK, st < en)) {
+              if (st < en) { atomicAdd (&cnt[(io + bpos[st]) & mask], 1u); ++my_hits; ++st; }
+            }
+          }
+        } else {
+          const uint32_t ib = ibase + pos;
+          const bool p0 = len > 0 && ib + e_0 < dlen, p1 = len > 1 && ib + e_1 < dlen, p2 = len > 2 && ib + e_2 < dlen, p3 = len > 3 && ib + e_3 < dlen;
+          QG_RED_IF (cnt + ((io + e_0) & mask), p0);
+          QG_RED_IF (cnt + ((io + e_1) & mask), p1);
+          QG_RED_IF (cnt + ((io + e_2) & mask), p2);
+          QG_RED_IF (cnt + ((io + e_3) & mask), p3);
+          my_hits += (uint32_t) p0 + (uint32_t) p1 + (uint32_t) p2 + (uint32_t) p3;
+          if (__any_sync (QG_FULL_MASK, len > 4)) {
+            uint32_t st = (uint32_t) bstart[code] + 4, en = len > 4 ? (uint32_t) bstart[code + 1] : 0u;
+            while (__any_sync (QG_FULL_MASK, st < en)) {
+              if (st < en) { const uint32_t v = bpos[st]; if (ib + v < dlen) { atomicAdd (&cnt[(io + v) & mask], 1u); ++my_hits; } ++st; }
+            }
+          }
+        }
+      }
+    }
+    __syncthreads ();
+    // diagonals below i1 - span can receive no further hits; windows end on a 4-slot boundary except the last one
+    const int i1 = (tb + QG_TILE_POS <= i_last + 1) ? tb + QG_TILE_POS : i_last + 1;    // exclusive
+    int emit_hi = (i1 > i_last) ? d_end : (i1 - span) - ((i1 + off) & 3);
+    if (emit_hi > d_end) emit_hi = d_end;
+    if (emit_hi > emit_lo) {
+      for (int base = emit_lo; base < emit_hi; base += QG_TSEED_ESTEP) {
+        uint32_t nib[2];
+        bool hot = false;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const int d0 = base + (q * T + tid) * 4;
+          nib[q] = 0;
+          if (d0 < emit_hi) {
+            uint4* p4 = (uint4*) (cnt + ((uint32_t) (d0 + spo) & mask));
+            const uint4 c = *p4;
+            *p4 = make_uint4 (0u, 0u, 0u, 0u);
+            const uint32_t cc[4] = { c.x, c.y, c.z, c.w };
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              if (d0 + e < emit_hi) {
+                if (COUNTS) counts_out[pd.count_off + (uint64_t) (d0 + e + span)] = cc[e];     // memory-guided mode: raw counts only
+                else if ((int) cc[e] >= threshold && cc[e] > 0) nib[q] |= 1u << e;
+              }
+            }
+          }
+          hot = hot || nib[q] != 0;
+        }
+        if (__syncthreads_or (hot ? 1 : 0)) {
+          for (int w = tid; w < QG_TSEED_ESTEP / 32; w += T) seedmask[w] = 0;
+          __syncthreads ();
+#pragma unroll
+          for (int q = 0; q < 2; ++q)
+            if (nib[q]) { const uint32_t bit = (uint32_t) (q * T + tid) * 4; atomicOr (&seedmask[bit >> 5], nib[q] << (bit & 31)); }
+          __syncthreads ();
+          if (tid == 0) {
+            // seeds in ascending order -> union of [seed-half, seed+half] clipped to the matrix (diagenv.cpp:79-84)
+            int open_lo = s_open_lo, open_hi = s_open_hi, have = s_have_open;
+            uint32_t nr = s_nruns;
+            for (int g = 0; g < QG_TSEED_ESTEP / 32; ++g) {
+              uint32_t m = seedmask[g];
+              while (m) {
+                const int bb = __ffs ((int) m) - 1;
+                m &= m - 1;
+                const int seed = base + g * 32 + bb;
+                int lo = seed - half_band, hi = seed + half_band;
+                if (lo < min_diag) lo = min_diag;
+                if (hi > max_diag) hi = max_diag;
+                if (have && lo <= open_hi + 1) { if (hi > open_hi) open_hi = hi; }
+                else {
+                  if (have) { if (nr < run_cap) item_runs[(size_t) blockIdx.x * run_cap + nr] = make_int2 (open_lo, open_hi); else *overflow_flag = 1; ++nr; }
+                  open_lo = lo; open_hi = hi; have = 1;
+                }
+              }
+            }
+            s_open_lo = open_lo; s_open_hi = open_hi; s_have_open = have; s_nruns = nr;
+          }
+          __syncthreads ();
+        }
+      }
+      __syncthreads ();
+      emit_lo = emit_hi;
+    }
+  }
+  if (tid == 0) {
+    uint32_t nr = s_nruns;
+    if (s_have_open) { if (nr < run_cap) item_runs[(size_t) blockIdx.x * run_cap + nr] = make_int2 (s_open_lo, s_open_hi); else *overflow_flag = 1; ++nr; }
+    item_nruns[blockIdx.x] = nr < run_cap ? nr : run_cap;
+  }
+  unsigned long long hits64 = my_hits;
+  for (int o = 16; o > 0; o >>= 1) hits64 += __shfl_down_sync (QG_FULL_MASK, hits64, o);
+  if (lane == 0 && hits64) atomicAdd (hit_counter, hits64);
+}
+
 // ---- merge item runs of a pair, add diagonal 0, count cells ---------------------------------------
 // One thread per pair (runs per pair are few).  pair_runs[pd.run_out ...] receives the final, sorted,
 // maximal runs; pair_info[p] = {n_runs, n_diagonals}; pair_cu[p] = iterated cells.

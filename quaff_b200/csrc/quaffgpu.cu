@@ -21,7 +21,7 @@ enum {
   SC_PAIRDESC = 0, SC_ITEMS, SC_ITEMRUNS, SC_ITEMNRUNS, SC_PAIRRUNS, SC_PAIRINFO, SC_PAIRCU, SC_FLAGS,
   SC_SEGS, SC_RPJOBS, SC_RP, SC_TRACE, SC_ENDVALS, SC_PAIRDP, SC_OUT0, SC_OUT1, SC_OUT2, SC_OUT3, SC_PATHSCR, SC_PATHOUT,
   SC_STORE, SC_ROWACC, SC_MISC0, SC_MISC1, SC_RQ, SC_RS, SC_ENDEX, SC_STOREEX, SC_ZM, SC_ZE,
-  SC_RPS, SC_XC64, SC_YC64, SC_KEYS0, SC_KEYS1, SC_VALS0, SC_VALS1, SC_IDXJOBS, SC_SEGOFF, SC_SORTTMP
+  SC_RPS, SC_XC64, SC_YC64, SC_KEYS0, SC_KEYS1, SC_VALS0, SC_VALS1, SC_IDXJOBS, SC_SEGOFF, SC_SORTTMP, SC_TILEJOBS
 };
 
 // ---- small helpers -----------------------------------------------------------------------------------
@@ -216,7 +216,7 @@ extern "C" int qg_set_seqs (qg_ctx* ctx, int which, size_t n, const uint8_t* tok
   if (qual) for (uint64_t t = 0; t < s.total; ++t) if (qual[t] >= QG_NQUAL) QG_FAIL (ctx, QG_ERR_INVALID, "qg_set_seqs: quality score %u out of range", qual[t]);
   s.h_tok.assign (tok, tok + s.total);
   if (qual) s.h_qual.assign (qual, qual + s.total); else s.h_qual.clear ();
-  s.codes_k = 0;
+  s.codes_k = 0; s.sorted_k = 0;
   // packed layout: each sequence starts on a word boundary and is followed by one zero word
   s.poff.resize (n + 1);
   uint64_t w = 0;
@@ -251,6 +251,29 @@ static int qg_ensure_codes (qg_ctx* ctx, int which, int k) {
     QG_TRY (qg_check_launch (ctx, "qg_codes_kernel"));
   }
   s.codes_k = k;
+  return QG_OK;
+}
+
+// the static side of the tile-sorted seeding kernel: every QG_TILE_POS positions of every sequence sorted by k-mer code
+static int qg_ensure_sorted (qg_ctx* ctx, int which, int k) {
+  qg_seqset& s = ctx->seqs[which];
+  QG_TRY (qg_ensure_codes (ctx, which, k));
+  if (s.sorted_k == k) return QG_OK;
+  std::vector<qg_tile_job> jobs;
+  for (size_t i = 0; i < s.n; ++i)
+    for (uint64_t b = s.off[i]; b < s.off[i + 1]; b += QG_TILE_POS) {
+      qg_tile_job jb; jb.off = b; jb.len = (uint32_t) std::min<uint64_t> (QG_TILE_POS, s.off[i + 1] - b); jb.pad_ = 0;
+      jobs.push_back (jb);
+    }
+  QG_TRY (qg_reserve (ctx, s.d_sorted, sizeof (uint32_t) * (s.total + 1)));
+  if (!jobs.empty ()) {
+    qg_timer tm (ctx, &ctx->stats.ms_prep);
+    QG_TRY (qg_upload (ctx, ctx->scratch[SC_TILEJOBS], jobs.data (), sizeof (qg_tile_job) * jobs.size ()));
+    QG_LAUNCH (qg_sort_tiles_kernel, (unsigned) jobs.size (), 256, 0, ctx->stream,
+               ctx->scratch[SC_TILEJOBS].as<qg_tile_job> (), s.d_codes.as<uint16_t> (), 1u << (2 * k), s.d_sorted.as<uint32_t> ());
+    QG_TRY (qg_check_launch (ctx, "qg_sort_tiles_kernel"));
+  }
+  s.sorted_k = k;
   return QG_OK;
 }
 
@@ -328,6 +351,15 @@ static size_t qg_seed_smem_bytes (int k, uint32_t ymax, uint32_t* ring_out) {
   while (ring < need) ring <<= 1;
   if (ring_out) *ring_out = ring;
   return (size_t) ring * 4 + (size_t) nk * 8 + (size_t) ((ymax + 2) & ~1u) * 2 + (QG_SEED_STEP / 32 + 2) * 4;
+}
+// the tile-sorted kernel (qg_seed_tile_kernel): k = 5 or 6, every read's diagonals fit the 32k-counter ring next to one tile
+static size_t qg_tseed_smem_bytes (int k, uint32_t ymax) {
+  const uint32_t nk = 1u << (2 * k);
+  return (size_t) QG_TSEED_RING * 4 + (size_t) (nk + 1) * 8 + (size_t) ((nk + 2 + 3) & ~3u) * 2 + (size_t) ((ymax + 2 + 1) & ~1u) * 2 + (QG_TSEED_ESTEP / 32 + 2) * 4;
+}
+static bool qg_seed_use_tiles (qg_ctx* ctx, int k, uint32_t ymax) {
+  if (getenv ("QG_SEED_LEGACY")) return false;                 // tests / profiling: the round-1 kernel
+  return (k == 5 || k == 6) && ymax >= (uint32_t) k && ymax - (uint32_t) k + 3 + QG_TILE_POS <= QG_TSEED_RING && qg_tseed_smem_bytes (k, ymax) <= ctx->smem_optin;
 }
 static bool qg_pair_is_sparse (const qg_dpconfig* cfg, uint32_t xlen, uint32_t ylen) {
   if (!cfg->sparse) return false;
@@ -407,12 +439,18 @@ static int qg_envelope_stage_cap (qg_ctx* ctx, const qg_dpconfig* cfg, uint64_t 
   uint64_t total_diags = 0;
   for (size_t p = 0; p < n_pairs; ++p) if (xi[p] < X.n && yi[p] < Y.n) total_diags += (uint64_t) X.len (xi[p]) + Y.len (yi[p]);
   int64_t chunk = (int64_t) (total_diags / (uint64_t) (16 * std::max (ctx->sm_count, 1)));
-  chunk = std::max<int64_t> (QG_SEED_CHUNK, std::min<int64_t> (chunk, 8 * QG_SEED_CHUNK));
-  chunk = (chunk / QG_SEED_STEP) * QG_SEED_STEP;
+  const int64_t chunk_min = (int64_t) qg_env_size ("QG_SEED_CHUNK", QG_SEED_CHUNK);      // lowered by the tests only: several items per pair on short inputs
+  chunk = std::max<int64_t> (chunk_min, std::min<int64_t> (chunk, 8 * chunk_min));
+  chunk = std::max<int64_t> (QG_SEED_STEP, (chunk / QG_SEED_STEP) * QG_SEED_STEP);
   const bool memory_mode = cfg->kmer_threshold < 0;
   if (cfg->sparse && (k < 1 || k > 32)) QG_FAIL (ctx, QG_ERR_INVALID, "-kmatch %d: k-mer length must be 1..32", k);
   const bool general = qg_seed_is_general (ctx, cfg, x_set, n_pairs, xi, yi);
   const int64_t gen_chunk = 32768;                               // reference positions per work item on the general path
+  uint32_t ymax_sparse = 0;
+  for (size_t p = 0; p < n_pairs; ++p)
+    if (xi[p] < X.n && yi[p] < Y.n && qg_pair_is_sparse (cfg, X.len (xi[p]), Y.len (yi[p]))) ymax_sparse = std::max (ymax_sparse, Y.len (yi[p]));
+  const bool tiles = !general && cfg->sparse && qg_seed_use_tiles (ctx, k, ymax_sparse);
+  if (tiles) chunk = std::max<int64_t> (QG_TILE_POS, (chunk / QG_TILE_POS) * QG_TILE_POS);   // item boundaries on tile boundaries
   std::vector<qg_index_job> idx_jobs; std::map<uint32_t, uint64_t> idx_of_read; uint64_t idx_total = 0;
   std::vector<uint32_t> mem_pairs;
   uint64_t count_total = 0, bits_total = 0, hist_total = 0;
@@ -451,6 +489,15 @@ static int qg_envelope_stage_cap (qg_ctx* ctx, const qg_dpconfig* cfg, uint64_t 
         d.idx_off = f->second;
       } else {
         const int64_t dmin = -((int64_t) d.ylen - k), dmax = (int64_t) d.xlen - k;   // diagonals that can receive hits
+        if (tiles) {
+          // [dmin, chunk), [chunk, 2 chunk), ...: every item but the first starts on a tile boundary of the reference
+          for (int64_t b = dmin; b <= dmax; ) {
+            const int64_t base = b < 0 ? 0 : b, e = base - base % chunk + chunk;
+            qg_seed_item it; it.pair = (uint32_t) p; it.d_begin = (int32_t) b; it.d_end = (int32_t) std::min<int64_t> (e, dmax + 1);
+            items.push_back (it);
+            b = e;
+          }
+        } else
         for (int64_t b = dmin; b <= dmax; b += chunk) {
           qg_seed_item it; it.pair = (uint32_t) p; it.d_begin = (int32_t) b; it.d_end = (int32_t) std::min<int64_t> (b + chunk, dmax + 1);
           items.push_back (it);
@@ -507,7 +554,21 @@ static int qg_envelope_stage_cap (qg_ctx* ctx, const qg_dpconfig* cfg, uint64_t 
     QG_TRY (qg_check_launch (ctx, "qg_seed_general_kernel"));
   }
   if (!items.empty ()) {
-    if (!general) {
+    if (tiles) {
+      QG_TRY (qg_ensure_sorted (ctx, x_set, k));
+      QG_TRY (qg_ensure_codes (ctx, QG_READS, k));
+      const size_t smem = qg_tseed_smem_bytes (k, ymax);
+      QG_CUDA (ctx, cudaFuncSetAttribute (qg_seed_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ctx->smem_optin));
+      QG_CUDA (ctx, cudaFuncSetAttribute (qg_seed_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ctx->smem_optin));
+      qg_timer tm (ctx, &ctx->stats.ms_seed);
+      auto kfn = memory_mode ? qg_seed_tile_kernel<true> : qg_seed_tile_kernel<false>;
+      QG_LAUNCH (kfn, (unsigned) items.size (), QG_TSEED_THREADS, smem, ctx->stream,
+                 dIT.as<qg_seed_item> (), dPD.as<qg_pair_desc> (), ctx->seqs[x_set].d_sorted.as<uint32_t> (), ctx->seqs[QG_READS].d_codes.as<uint16_t> (),
+                 k, cfg->kmer_threshold, (int) ((unsigned) cfg->band_size / 2), ymax, run_cap,
+                 dIR.as<int2> (), dIN.as<uint32_t> (), (unsigned long long*) ((char*) dFL.p + 8), (uint32_t*) dFL.p,
+                 memory_mode ? ctx->scratch[SC_STORE].as<uint32_t> () : (uint32_t*) nullptr);
+      QG_TRY (qg_check_launch (ctx, "qg_seed_tile_kernel"));
+    } else if (!general) {
     QG_TRY (qg_ensure_codes (ctx, x_set, k));
     QG_TRY (qg_ensure_codes (ctx, QG_READS, k));
     uint32_t ring = 1;
@@ -580,7 +641,7 @@ static int qg_envelope_stage_cap (qg_ctx* ctx, const qg_dpconfig* cfg, uint64_t 
 static int qg_envelope_stage_retry (qg_ctx* ctx, const qg_dpconfig* cfg, uint64_t cell_size, int x_set,
                                     size_t n_pairs, const uint32_t* xi, const uint32_t* yi, qg_env_result& out) {
   const uint32_t half = (uint32_t) cfg->band_size / 2;
-  const uint32_t cap_max = 8 * QG_SEED_CHUNK / (2 * half + 2) + 3;
+  const uint32_t cap_max = (8 * QG_SEED_CHUNK + 65536) / (2 * half + 2) + 3;      // the tile kernel's first item also owns the read's negative diagonals
   uint32_t cap = (uint32_t) qg_env_size ("QG_RUN_CAP", 16);
   while (true) {
     bool overflow = false;

@@ -43,6 +43,19 @@ def test_emu_threshold_zero(emu, oracle, workload, monkeypatch):
     pc.check_envelopes(emu, oracle, x, reads, api.dp_config(kmer_threshold=0, band_size=4), xi, yi)
 
 
+def test_emu_tile_seeding_item_boundaries(emu, oracle, workload, monkeypatch):
+    """the tile-sorted seeding kernel with several work items per pair: edge tiles, interior tiles, the ring offset of items
+    that do not start on a 4-diagonal boundary; fixed threshold and memory-guided mode"""
+    x, reads, _ = workload
+    xi, yi = pc.all_pairs(len(x), len(reads))
+    monkeypatch.setenv("QG_SEED_CHUNK", "1024")
+    pc.check_envelopes(emu, oracle, x, reads, api.dp_config(kmer_threshold=6), xi, yi)
+    pc.check_envelopes(emu, oracle, x, reads, api.dp_config(kmer_threshold=3, kmer_len=5, band_size=10), xi, yi)
+    pc.check_envelopes(emu, oracle, x, reads, api.dp_config(kmer_threshold=-1, max_size=200_000), xi, yi)
+    monkeypatch.setenv("QG_SEED_LEGACY", "1")                       # the round-1 kernel stays the fallback for long reads / k = 7
+    pc.check_envelopes(emu, oracle, x, reads, api.dp_config(kmer_threshold=6), xi, yi)
+
+
 def test_emu_viterbi_forward(emu, oracle, workload):
     x, reads, s_or = workload
     xi, yi = pc.all_pairs(len(x), len(reads))
