@@ -104,11 +104,15 @@ def make_workload(rank: int, n_batches: int, reads_per_step: int, ref_len: int =
     return add_revcomps([ref]), batches
 
 
+PARAMS_JSON = os.path.join(ROOT, "tests", "golden", "defaultparams.json")
+NULL_JSON = os.path.join(ROOT, "tests", "golden", "testquaffnullparams.json")
+
+
 def load_models():
+    """The model files both arms read.  quaff_b200.params parses JSON numbers the way the reference's parser does (gason), so the
+    GPU arm computes with exactly the values `quaff -params ... -null ...` holds after reading the same two files."""
     from quaff_b200.params import QuaffNullParams, QuaffParams
-    qp = QuaffParams.load(os.path.join(ROOT, "tests", "golden", "defaultparams.json"))
-    nullp = QuaffNullParams.load(os.path.join(ROOT, "tests", "golden", "testquaffnullparams.json"))
-    return qp, nullp
+    return QuaffParams.load(PARAMS_JSON), QuaffNullParams.load(NULL_JSON)
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -129,7 +133,7 @@ def reference_cpu_run(n_reads: int, threads: int, ref_len: int = REF_LEN, read_l
             with open(fq, "w") as fh:
                 for r in reads:
                     fh.write(f"@{r.name}\n{r.seq}\n+\n{r.qual}\n")
-            open(pj, "w").write(qp.to_json()); open(nj, "w").write(nullp.to_json())
+            open(pj, "w").write(open(PARAMS_JSON).read()); open(nj, "w").write(open(NULL_JSON).read())      # the same text the GPU arm parsed
             cmd = [po.REF_QUAFF, "align", fa, fq, "-params", pj, "-null", nj, "-kmatchband", "64", "-format", "sam", "-threads", str(threads)]
             t0 = time.time()
             res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
@@ -255,7 +259,7 @@ def run_cfg5(args):
                     open(fa, "w").write(f">{ref.name}\n{ref.seq}\n")
                     r0 = batches[0][0]
                     open(fq, "w").write(f"@{r0.name}\n{r0.seq}\n+\n{r0.qual}\n")
-                    open(pj, "w").write(qp.to_json()); open(nj, "w").write(nullp.to_json())
+                    open(pj, "w").write(open(PARAMS_JSON).read()); open(nj, "w").write(open(NULL_JSON).read())
                     tc = time.time()
                     res = subprocess.run([po.REF_QUAFF, "align", fa, fq, "-params", pj, "-null", nj, "-kmatchoff", "-format", "sam", "-threads", "2"],
                                          stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)

@@ -122,8 +122,14 @@ struct qg_ctx {
   qg_dbuf scratch[48];
   int fb_exact = 0;                  // QG_OPT_FB_EXACT
   cudaEvent_t ev_sync = nullptr;     // blocking host waits (qg_sync)
-  void* h_pinned = nullptr;          // pinned staging for large device-to-host copies
-  size_t h_pinned_cap = 0;
+  // stage timers do not block: the event pairs wait here until the next host synchronisation resolves them
+  struct pending_timer { cudaEvent_t a, b; double* acc; };
+  std::vector<pending_timer> timers;
+  std::vector<cudaEvent_t> ev_pool;
+  void* h_pinned = nullptr;          // pinned staging for device-to-host copies
+  size_t h_pinned_cap = 0, h_pinned_used = 0;
+  struct pending_fetch { void* dst; size_t off, bytes; };
+  std::vector<pending_fetch> fetches;  // copies queued into h_pinned, delivered by qg_fetch_wait after ONE host synchronisation
 };
 
 static inline int qg_reserve (qg_ctx* ctx, qg_dbuf& b, size_t bytes) {

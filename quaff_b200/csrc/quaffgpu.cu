@@ -38,34 +38,69 @@ static void qg_htrace (const char* label) {
 
 // Host waits sleep on a blocking event instead of spinning in cudaStreamSynchronize: several contexts (host threads) share
 // one GPU, and spinning waiters burn the cores (and any CPU quota) the other contexts' host work needs.
+static cudaEvent_t qg_event_get (qg_ctx* ctx) {
+  if (!ctx->ev_pool.empty ()) { cudaEvent_t e = ctx->ev_pool.back (); ctx->ev_pool.pop_back (); return e; }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate (&e);
+  return e;
+}
+// the stream has just been synchronised: every recorded timer event is complete
+static void qg_resolve_timers (qg_ctx* ctx) {
+  for (auto& t : ctx->timers) {
+    float ms = 0;
+    if (t.a && t.b && cudaEventElapsedTime (&ms, t.a, t.b) == cudaSuccess) *t.acc += ms;
+    if (t.a) ctx->ev_pool.push_back (t.a);
+    if (t.b) ctx->ev_pool.push_back (t.b);
+  }
+  ctx->timers.clear ();
+}
 static cudaError_t qg_sync (qg_ctx* ctx) {
   static const bool spin = getenv ("QG_SPIN_SYNC") != nullptr;
-  if (spin) return cudaStreamSynchronize (ctx->stream);
-  cudaError_t e = cudaEventRecord (ctx->ev_sync, ctx->stream);
-  if (e != cudaSuccess) return e;
-  return cudaEventSynchronize (ctx->ev_sync);
+  cudaError_t e;
+  if (spin) e = cudaStreamSynchronize (ctx->stream);
+  else {
+    e = cudaEventRecord (ctx->ev_sync, ctx->stream);
+    if (e != cudaSuccess) return e;
+    e = cudaEventSynchronize (ctx->ev_sync);
+  }
+  if (e == cudaSuccess) qg_resolve_timers (ctx);
+  return e;
 }
 static int qg_upload (qg_ctx* ctx, qg_dbuf& b, const void* src, size_t bytes) {
   QG_TRY (qg_reserve (ctx, b, bytes));
   if (bytes) QG_CUDA (ctx, cudaMemcpyAsync (b.p, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
   return QG_OK;
 }
-static int qg_download (qg_ctx* ctx, void* dst, const void* src, size_t bytes) {
-  if (bytes >= (256u << 10)) {
-    // large results go through a pinned staging buffer (DMA at link speed), then one host memcpy
-    if (ctx->h_pinned_cap < bytes) {
-      if (ctx->h_pinned) { cudaFreeHost (ctx->h_pinned); ctx->h_pinned = nullptr; ctx->h_pinned_cap = 0; }
-      QG_CUDA (ctx, cudaMallocHost (&ctx->h_pinned, bytes + bytes / 4));
-      ctx->h_pinned_cap = bytes + bytes / 4;
-    }
-    QG_CUDA (ctx, cudaMemcpyAsync (ctx->h_pinned, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
-    QG_CUDA (ctx, qg_sync (ctx));
-    memcpy (dst, ctx->h_pinned, bytes);
-    return QG_OK;
-  }
-  if (bytes) QG_CUDA (ctx, cudaMemcpyAsync (dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+// Device-to-host results: qg_fetch queues a copy into the pinned staging buffer, qg_fetch_wait synchronises ONCE and hands
+// every queued piece to its destination (a pageable cudaMemcpyAsync would stall the host per call).
+static int qg_fetch_wait (qg_ctx* ctx) {
   QG_CUDA (ctx, qg_sync (ctx));
+  for (const auto& f : ctx->fetches) memcpy (f.dst, (const char*) ctx->h_pinned + f.off, f.bytes);
+  ctx->fetches.clear ();
+  ctx->h_pinned_used = 0;
   return QG_OK;
+}
+static int qg_fetch (qg_ctx* ctx, void* dst, const void* src, size_t bytes) {
+  if (!bytes) return QG_OK;
+  const size_t need = (bytes + 255) & ~(size_t) 255;
+  if (ctx->h_pinned_used + need > ctx->h_pinned_cap) {
+    if (!ctx->fetches.empty ()) QG_TRY (qg_fetch_wait (ctx));      // deliver what is queued before the buffer moves
+    if (need > ctx->h_pinned_cap) {
+      if (ctx->h_pinned) { cudaFreeHost (ctx->h_pinned); ctx->h_pinned = nullptr; ctx->h_pinned_cap = 0; }
+      const size_t want = std::max<size_t> (need + need / 4, (size_t) 1 << 20);
+      QG_CUDA (ctx, cudaMallocHost (&ctx->h_pinned, want));
+      ctx->h_pinned_cap = want;
+    }
+  }
+  QG_CUDA (ctx, cudaMemcpyAsync ((char*) ctx->h_pinned + ctx->h_pinned_used, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  qg_ctx::pending_fetch f; f.dst = dst; f.off = ctx->h_pinned_used; f.bytes = bytes;
+  ctx->fetches.push_back (f);
+  ctx->h_pinned_used += need;
+  return QG_OK;
+}
+static int qg_download (qg_ctx* ctx, void* dst, const void* src, size_t bytes) {
+  QG_TRY (qg_fetch (ctx, dst, src, bytes));
+  return qg_fetch_wait (ctx);
 }
 static int qg_check_launch (qg_ctx* ctx, const char* what) {
   cudaError_t e = cudaGetLastError ();
@@ -73,14 +108,15 @@ static int qg_check_launch (qg_ctx* ctx, const char* what) {
   ctx->stats.kernel_launches += 1;
   return QG_OK;
 }
+// device time of a stage, by CUDA events on the launching stream; never blocks the host (resolved at the next qg_sync)
 struct qg_timer {
-  qg_ctx* ctx; double* acc;
-  qg_timer (qg_ctx* c, double* a) : ctx (c), acc (a) { cudaEventRecord (ctx->ev[0], ctx->stream); }
+  qg_ctx* ctx; double* acc; cudaEvent_t a;
+  qg_timer (qg_ctx* c, double* acc_) : ctx (c), acc (acc_), a (qg_event_get (c)) { if (a) cudaEventRecord (a, ctx->stream); }
   ~qg_timer () {
-    cudaEventRecord (ctx->ev[1], ctx->stream);
-    cudaEventSynchronize (ctx->ev[1]);
-    float ms = 0; cudaEventElapsedTime (&ms, ctx->ev[0], ctx->ev[1]);
-    *acc += ms;
+    cudaEvent_t b = qg_event_get (ctx);
+    if (b) cudaEventRecord (b, ctx->stream);
+    qg_ctx::pending_timer t; t.a = a; t.b = b; t.acc = acc;
+    ctx->timers.push_back (t);
   }
 };
 // the launch classes of one DP stage (different R / warp counts) are independent: run them side by side
@@ -164,7 +200,7 @@ extern "C" void qg_destroy (qg_ctx* ctx) {
   cudaSetDevice (ctx->device);
   qg_sync (ctx);
   auto rel = [] (qg_dbuf& b) { if (b.p) cudaFree (b.p); b.p = nullptr; b.cap = 0; };
-  for (auto& s : ctx->seqs) { rel (s.d_tok); rel (s.d_qual); rel (s.d_off); rel (s.d_packed); rel (s.d_poff); rel (s.d_codes); }
+  for (auto& s : ctx->seqs) { rel (s.d_tok); rel (s.d_qual); rel (s.d_off); rel (s.d_packed); rel (s.d_poff); rel (s.d_codes); rel (s.d_sorted); }
   rel (ctx->model.d_match); rel (ctx->model.d_insert); rel (ctx->model.d_gap);
   rel (ctx->omodel.d_match); rel (ctx->omodel.d_insert); rel (ctx->omodel.d_m2m); rel (ctx->omodel.d_m2i); rel (ctx->omodel.d_m2d);
   for (int s = 0; s < 2; ++s) { rel (ctx->omodel.d_pair[s]); rel (ctx->omodel.d_xonly[s]); rel (ctx->omodel.d_yonly[s]); rel (ctx->omodel.d_none[s]); }
@@ -172,6 +208,7 @@ extern "C" void qg_destroy (qg_ctx* ctx) {
   if (ctx->h_pinned) cudaFreeHost (ctx->h_pinned);
   for (auto& b : ctx->scratch) rel (b);
   cudaEventDestroy (ctx->ev[0]); cudaEventDestroy (ctx->ev[1]);
+  for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy (e);
   cudaEventDestroy (ctx->ev_fork); if (ctx->ev_sync) cudaEventDestroy (ctx->ev_sync);
   for (int i = 0; i < 8; ++i) { cudaStreamDestroy (ctx->side[i]); cudaEventDestroy (ctx->ev_join[i]); }
   cudaStreamDestroy (ctx->stream);
@@ -186,6 +223,8 @@ extern "C" int qg_set_option (qg_ctx* ctx, int option, int64_t value) {
 
 extern "C" int qg_get_stats (qg_ctx* ctx, qg_stats* out, int reset) {
   if (!ctx || !out) return QG_ERR_INVALID;
+  cudaSetDevice (ctx->device);
+  QG_CUDA (ctx, qg_sync (ctx));                              // resolves the pending stage timers
   *out = ctx->stats;
   if (reset) memset (&ctx->stats, 0, sizeof (ctx->stats));
   return QG_OK;
@@ -614,10 +653,11 @@ static int qg_envelope_stage_cap (qg_ctx* ctx, const qg_dpconfig* cfg, uint64_t 
   std::vector<int2> pr (run_total + 1);
   {
     qg_timer tm (ctx, &ctx->stats.ms_d2h);
-    QG_TRY (qg_download (ctx, flags, dFL.p, 16));
-    QG_TRY (qg_download (ctx, info.data (), dPI.p, sizeof (uint2) * n_pairs));
-    QG_TRY (qg_download (ctx, cu.data (), dPC.p, sizeof (unsigned long long) * n_pairs));
-    QG_TRY (qg_download (ctx, pr.data (), dPR.p, sizeof (int2) * run_total));
+    QG_TRY (qg_fetch (ctx, flags, dFL.p, 16));
+    QG_TRY (qg_fetch (ctx, info.data (), dPI.p, sizeof (uint2) * n_pairs));
+    QG_TRY (qg_fetch (ctx, cu.data (), dPC.p, sizeof (unsigned long long) * n_pairs));
+    QG_TRY (qg_fetch (ctx, pr.data (), dPR.p, sizeof (int2) * run_total));
+    QG_TRY (qg_fetch_wait (ctx));
   }
   if ((uint32_t) flags[0] == 2) QG_FAIL (ctx, QG_ERR_CUDA, "internal: memory-guided envelope produced more runs than the bound");
   if ((uint32_t) flags[0]) { *overflow = true; return QG_OK; }
@@ -1030,10 +1070,11 @@ static int qg_wide_run (qg_ctx* ctx, const qg_dpconfig* cfg, const qg_env_result
                    ctx->scratch[SC_OUT3].as<uint32_t> (), (uint32_t*) ctx->scratch[SC_FLAGS].p);
         QG_TRY (qg_check_launch (ctx, "qg_wide_traceback_kernel"));
       }
-      QG_TRY (qg_download (ctx, xs.data (), ctx->scratch[SC_OUT1].p, sizeof (uint32_t) * np));
-      QG_TRY (qg_download (ctx, xe.data (), ctx->scratch[SC_OUT2].p, sizeof (uint32_t) * np));
-      QG_TRY (qg_download (ctx, plen.data (), ctx->scratch[SC_OUT3].p, sizeof (uint32_t) * np));
-      QG_TRY (qg_download (ctx, &flag, ctx->scratch[SC_FLAGS].p, sizeof (uint32_t)));
+      QG_TRY (qg_fetch (ctx, xs.data (), ctx->scratch[SC_OUT1].p, sizeof (uint32_t) * np));
+      QG_TRY (qg_fetch (ctx, xe.data (), ctx->scratch[SC_OUT2].p, sizeof (uint32_t) * np));
+      QG_TRY (qg_fetch (ctx, plen.data (), ctx->scratch[SC_OUT3].p, sizeof (uint32_t) * np));
+      QG_TRY (qg_fetch (ctx, &flag, ctx->scratch[SC_FLAGS].p, sizeof (uint32_t)));
+      QG_TRY (qg_fetch_wait (ctx));
       if (flag) QG_FAIL (ctx, QG_ERR_CUDA, "internal: tiled traceback left the envelope (code %u)", flag);
       std::vector<uint64_t> goff (np + 1, 0);
       for (size_t q = 0; q < np; ++q) goff[q + 1] = goff[q] + plen[q];
@@ -1218,10 +1259,11 @@ static int qg_viterbi_impl (qg_ctx* ctx, const qg_dpconfig* cfg, size_t n_pairs,
       }
       {
         qg_timer tm (ctx, &ctx->stats.ms_d2h);
-        QG_TRY (qg_download (ctx, xs.data (), ctx->scratch[SC_OUT1].p, sizeof (uint32_t) * np));
-        QG_TRY (qg_download (ctx, xe.data (), ctx->scratch[SC_OUT2].p, sizeof (uint32_t) * np));
-        QG_TRY (qg_download (ctx, plen.data (), ctx->scratch[SC_OUT3].p, sizeof (uint32_t) * np));
-        QG_TRY (qg_download (ctx, &flag, ctx->scratch[SC_FLAGS].p, sizeof (uint32_t)));
+        QG_TRY (qg_fetch (ctx, xs.data (), ctx->scratch[SC_OUT1].p, sizeof (uint32_t) * np));
+        QG_TRY (qg_fetch (ctx, xe.data (), ctx->scratch[SC_OUT2].p, sizeof (uint32_t) * np));
+        QG_TRY (qg_fetch (ctx, plen.data (), ctx->scratch[SC_OUT3].p, sizeof (uint32_t) * np));
+        QG_TRY (qg_fetch (ctx, &flag, ctx->scratch[SC_FLAGS].p, sizeof (uint32_t)));
+        QG_TRY (qg_fetch_wait (ctx));
       }
       if (flag) QG_FAIL (ctx, QG_ERR_CUDA, "internal: traceback left the envelope (code %u)", flag);
       for (size_t p = 0; p < np; ++p) {
@@ -1605,9 +1647,10 @@ extern "C" int qg_backward_counts (qg_ctx* ctx, const qg_dpconfig* cfg, size_t n
     }
     {
       qg_timer tm (ctx, &ctx->stats.ms_d2h);
-      if (fwd_loglike) QG_TRY (qg_download (ctx, fwd_loglike + p0, ctx->scratch[SC_OUT0].p, sizeof (double) * np));
-      if (back_loglike) QG_TRY (qg_download (ctx, back_loglike + p0, ctx->scratch[SC_OUT1].p, sizeof (double) * np));
-      if (counts_per_pair) QG_TRY (qg_download (ctx, counts_per_pair + (uint64_t) p0 * nC, ctx->scratch[SC_PATHSCR].p, sizeof (double) * nC * np));
+      if (fwd_loglike) QG_TRY (qg_fetch (ctx, fwd_loglike + p0, ctx->scratch[SC_OUT0].p, sizeof (double) * np));
+      if (back_loglike) QG_TRY (qg_fetch (ctx, back_loglike + p0, ctx->scratch[SC_OUT1].p, sizeof (double) * np));
+      if (counts_per_pair) QG_TRY (qg_fetch (ctx, counts_per_pair + (uint64_t) p0 * nC, ctx->scratch[SC_PATHSCR].p, sizeof (double) * nC * np));
+      QG_TRY (qg_fetch_wait (ctx));
     }
     p0 = p1;
   }
@@ -1901,10 +1944,11 @@ extern "C" int qg_overlap_viterbi (qg_ctx* ctx, const qg_dpconfig* cfg, size_t n
     }
     {
       qg_timer tm (ctx, &ctx->stats.ms_d2h);
-      QG_TRY (qg_download (ctx, score + p0, ctx->scratch[SC_OUT0].p, sizeof (double) * np));
-      QG_TRY (qg_download (ctx, co.data (), ctx->scratch[SC_OUT2].p, sizeof (uint32_t) * 4 * np));
-      QG_TRY (qg_download (ctx, plen.data (), ctx->scratch[SC_OUT3].p, sizeof (uint32_t) * np));
-      QG_TRY (qg_download (ctx, &flag, ctx->scratch[SC_FLAGS].p, sizeof (uint32_t)));
+      QG_TRY (qg_fetch (ctx, score + p0, ctx->scratch[SC_OUT0].p, sizeof (double) * np));
+      QG_TRY (qg_fetch (ctx, co.data (), ctx->scratch[SC_OUT2].p, sizeof (uint32_t) * 4 * np));
+      QG_TRY (qg_fetch (ctx, plen.data (), ctx->scratch[SC_OUT3].p, sizeof (uint32_t) * np));
+      QG_TRY (qg_fetch (ctx, &flag, ctx->scratch[SC_FLAGS].p, sizeof (uint32_t)));
+      QG_TRY (qg_fetch_wait (ctx));
     }
     if (flag) QG_FAIL (ctx, QG_ERR_CUDA, "internal: overlap traceback left the envelope (code %u)", flag);
     if (coords4) memcpy (coords4 + 4 * p0, co.data (), sizeof (uint32_t) * 4 * np);

@@ -15,6 +15,52 @@ import numpy as np
 from .seqs import DNA
 
 
+def gason_double(text: str) -> float:
+    """A JSON number as the reference's parser reads it (gason's string2double, src/gason.cpp:73-117): digits are
+    accumulated in double arithmetic -- result*10 + d, then d * 0.1^n for the fraction, then a squared-base power for the
+    exponent -- which is NOT correctly rounded: the value can differ from strtod's by an ulp or two.  IEEE double
+    operations are the same here and there, so this returns the reference's value bit for bit; the parameters the GPU
+    path gets from a JSON file are then exactly the ones `quaff` computes with from the same file (score ties in the
+    Viterbi traceback are decided in the last bit)."""
+    s = text.strip()
+    n = len(s)
+    i = 0
+    neg = i < n and s[i] == "-"
+    if neg:
+        i += 1
+    result = 0.0
+    while i < n and s[i].isdigit():
+        result = (result * 10) + (ord(s[i]) - 48); i += 1
+    if i < n and s[i] == ".":
+        i += 1
+        fraction = 1.0
+        while i < n and s[i].isdigit():
+            fraction *= 0.1
+            result += (ord(s[i]) - 48) * fraction; i += 1
+    if i < n and s[i] in "eE":
+        i += 1
+        base = 10.0
+        if i < n and s[i] == "+":
+            i += 1
+        elif i < n and s[i] == "-":
+            i += 1; base = 0.1
+        exponent = 0
+        while i < n and s[i].isdigit():
+            exponent = exponent * 10 + (ord(s[i]) - 48); i += 1
+        power = 1.0
+        while exponent:
+            if exponent & 1:
+                power *= base
+            exponent >>= 1; base *= base
+        result *= power
+    return -result if neg else result
+
+
+def _loads(text: str):
+    """json.loads with every number read the reference's way"""
+    return json.loads(text, parse_float=gason_double, parse_int=gason_double)
+
+
 def kmer_string(kmer: int, k: int) -> str:
     """kmerToString (fastseq.cpp:44-49): first base most significant."""
     s = []
@@ -68,7 +114,7 @@ class QuaffParams:
     # ---- JSON -------------------------------------------------------------------------------
     @staticmethod
     def from_json(text: str) -> "QuaffParams":
-        jm = json.loads(text)
+        jm = _loads(text)
         mk = int(jm.get("matchOrder", 1))
         gk = int(jm.get("gapOrder", 0))
         qp = QuaffParams(match_k=mk, gap_k=gk)
@@ -134,7 +180,7 @@ class QuaffNullParams:
 
     @staticmethod
     def from_json(text: str) -> "QuaffNullParams":
-        jm = json.loads(text)
+        jm = _loads(text)
         np_ = QuaffNullParams(null_emit=float(jm["nullEmit"]))
         for i in range(4):
             d = jm["null"][DNA[i]]

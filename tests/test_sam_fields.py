@@ -29,7 +29,8 @@ def test_sam_fields_match_reference_cli(oracle, tmp_path):
     fa, fq, pj, nj = (str(tmp_path / n) for n in ("ref.fa", "reads.fq", "params.json", "null.json"))
     open(fa, "w").write(f">{x[0].name}\n{x[0].seq}\n")
     open(fq, "w").write("".join(f"@{r.name}\n{r.seq}\n+\n{r.qual}\n" for r in reads))
-    open(pj, "w").write(qp.to_json()); open(nj, "w").write(nullp.to_json())
+    # the SAME model text on both sides: quaff_b200.params reads JSON numbers the way the reference's parser does
+    open(pj, "w").write(open(os.path.join(gc.GOLD, "defaultparams.json")).read()); open(nj, "w").write(open(os.path.join(gc.GOLD, "testquaffnullparams.json")).read())
     res = subprocess.run([po.REF_QUAFF, "align", fa, fq, "-params", pj, "-null", nj, "-kmatchn", "10", "-format", "sam", "-threads", "1"],
                          stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
     assert res.returncode == 0, res.stderr[-500:]
@@ -52,3 +53,25 @@ def test_sam_fields_match_reference_cli(oracle, tmp_path):
     result["x_start"][0] += 1
     with pytest.raises(AssertionError):
         sam.compare_batch(res.stdout, reads, x[0].name, len(x[0]), result)
+
+
+def test_gason_number_parsing():
+    """JSON numbers as the reference reads them (gason string2double, src/gason.cpp:73-117): not correctly rounded"""
+    from quaff_b200.params import gason_double
+    assert gason_double("0.1") == 0.1 and gason_double("47") == 47.0 and gason_double("-2.5e1") == -25.0
+    assert gason_double("0.3") == 3 * 0.1 and gason_double("0.3") != 0.3
+    assert gason_double("1e-2") == 0.1 * 0.1 and gason_double("12.5E+1") == 125.0
+
+
+def test_params_load_equals_reference_parse(ref):
+    from quaff_b200.params import QuaffParams, random_params
+    texts = [open(os.path.join(gc.GOLD, n)).read() for n in ("defaultparams.json", "testquaffparams.json")]
+    texts.append(random_params(np.random.default_rng(1), 2, 1).to_json())
+    for text in texts:
+        qp = QuaffParams.from_json(text)
+        hp = ref.L.qref_params_from_json(text.encode())
+        qr = ref.params_as_parsed(hp, qp)
+        assert np.array_equal(qp.begin_insert, qr.begin_insert) and np.array_equal(qp.begin_delete, qr.begin_delete)
+        assert (qp.extend_insert, qp.extend_delete) == (qr.extend_insert, qr.extend_delete)
+        for a, b in list(zip(qp.insert, qr.insert)) + [(a, b) for ra, rb in zip(qp.match, qr.match) for a, b in zip(ra, rb)]:
+            assert (a.p, a.q, a.r) == (b.p, b.q, b.r)
