@@ -311,23 +311,24 @@ qg_sort_tiles_kernel (const qg_tile_job* __restrict__ jobs, const uint16_t* __re
   for (uint32_t c = cb; c < ce; ++c) { const uint32_t v = cnt[c]; cnt[c] = run; run += v; }
   __syncthreads ();
   for (uint32_t p = tid; p < jb.len; p += 256) {
-    const uint32_t c16 = codes[jb.off + p];
-    const uint32_t slot = atomicAdd (&cnt[c16 > nk ? nk : c16], 1u);
-    sorted[jb.off + slot] = (c16 << 16) | p;
+    uint32_t c = codes[jb.off + p]; if (c > nk) c = nk;            // nk: no k-mer starts here (the empty header)
+    const uint32_t slot = atomicAdd (&cnt[c], 1u);
+    sorted[jb.off + slot] = (c << 16) | (p << 2);                  // position pre-scaled to a byte offset into the counter ring
   }
 }
 
-#ifdef QG_EMU
-#define QG_RED_IF(addr, pred) do { if (pred) atomicAdd ((addr), 1u); } while (0)
-#else
-#define QG_RED_IF(addr, pred) asm volatile ("{ .reg .pred q; setp.ne.u32 q, %1, 0; @q red.shared.add.u32 [%0], 1; }" \
-    :: "r" ((uint32_t) __cvta_generic_to_shared (addr)), "r" ((uint32_t) (pred)) : "memory")
-#endif
+// One shared-memory increment at byte offset `boff` of the ring if `pred`, else on the lane's own dummy word: ptxas turns
+// a PREDICATED shared atomic into a divergent branch around it (BSSY / BRA / ATOMS / BSYNC, measured: 8 instructions per
+// slot), a select between two addresses costs one.
+#define QG_RED_IF(cnt, boff, pred, dummy_off) atomicAdd ((uint32_t*) ((char*) (cnt) + ((pred) ? (boff) : (dummy_off))), 1u)
 
-// shared memory: cnt[QG_TSEED_RING] u32 | hdr[nk + 1] uint2 | bstart[nk + 2] u16 | bpos[ymax + 2] u16 | seedmask[ESTEP/32 + 2] u32
-//   hdr[code]  = first four bucket entries (14 bit each) | min(length, 255) << 56; hdr[nk] = empty (positions without a k-mer)
+// shared memory: cnt[QG_TSEED_RING] u32 | hdr[nk + 1] uint2 | bstart[nk + 2] u16 | bpos[ymax + 2] u16 | seedmask[ESTEP/32 + 2] u32 | dummy[32] u32
+//   hdr[code]  = the first four bucket entries as 16-bit fields holding 4 * (span - j), the byte offset a hit adds to the ring
+//                address; 0xFFFF = empty slot; bit 0 of field 3 = "the bucket has more than four entries"; hdr[nk] = all empty
+//                (positions without a k-mer)
 //   bpos       = span - j for every k-mer start j of the read, bucket by bucket; bstart[code] = first entry of the bucket
 //   ring slot of diagonal d = (d + span + off) & (ring - 1); off in 0..3 makes the item's first diagonal 16-byte aligned
+// The hit statistic is the sum of the counters the emit scan reads (every hit of the item is one increment of one of them).
 template<bool COUNTS>
 __global__ void __launch_bounds__ (QG_TSEED_THREADS, 1)
 qg_seed_tile_kernel (const qg_seed_item* __restrict__ items, const qg_pair_desc* __restrict__ pairs,
@@ -344,6 +345,7 @@ qg_seed_tile_kernel (const qg_seed_item* __restrict__ items, const qg_pair_desc*
   uint16_t* bstart = (uint16_t*) (hdr + nk + 1);
   uint16_t* bpos = bstart + ((nk + 2 + 3) & ~3u);
   uint32_t* seedmask = (uint32_t*) (bpos + ((ymax + 2 + 1) & ~1u));
+  const uint32_t dummy_off = (uint32_t) ((char*) (seedmask + QG_TSEED_ESTEP / 32 + 2) - (char*) cnt) + 4u * (threadIdx.x & 31);   // one word per lane: no bank conflict among them
   __shared__ uint32_t s_warp_tot[T / 32];
   __shared__ int s_open_lo, s_open_hi, s_have_open;
   __shared__ uint32_t s_nruns;
@@ -380,11 +382,12 @@ qg_seed_tile_kernel (const qg_seed_item* __restrict__ items, const qg_pair_desc*
   __syncthreads ();
   for (uint32_t c = cb; c < ce; ++c) {
     const uint32_t st = bstart[c], len = (uint32_t) bstart[c + 1] - st;
-    unsigned long long v = (unsigned long long) (len < 255u ? len : 255u) << 56;
-    for (uint32_t t = 0; t < 4 && t < len; ++t) v |= (unsigned long long) bpos[st + t] << (14 * t);
-    hdr[c] = make_uint2 ((uint32_t) v, (uint32_t) (v >> 32));
+    uint32_t f[4];
+    for (uint32_t t = 0; t < 4; ++t) f[t] = t < len ? (uint32_t) bpos[st + t] << 2 : 0xFFFFu;
+    if (len > 4) f[3] |= 1u;
+    hdr[c] = make_uint2 (f[0] | (f[1] << 16), f[2] | (f[3] << 16));
   }
-  if (tid == 0) hdr[nk] = make_uint2 (0u, 0u);
+  if (tid == 0) hdr[nk] = make_uint2 (0xFFFFFFFFu, 0xFFFFFFFFu);
   for (uint32_t c = tid; c < ring; c += T) cnt[c] = 0;
   __syncthreads ();
 
@@ -398,52 +401,48 @@ qg_seed_tile_kernel (const qg_seed_item* __restrict__ items, const qg_pair_desc*
   const int off = (4 - ((d_begin + span) & 3)) & 3;
   const int spo = span + off;                             // (d_begin + spo) is a multiple of 4
   int emit_lo = d_begin;
-  uint32_t my_hits = 0;                                   // per thread: at most (chunk + span) / T positions x bucket length
+  const uint32_t mask4 = mask << 2, dlen4 = dlen << 2;
+  uint32_t my_hits = 0;                                   // per thread: sums of at most (chunk / T) windows of counters
 
   for (int tile = i_begin / QG_TILE_POS; tile <= i_last / QG_TILE_POS; ++tile) {
     const int tb = tile * QG_TILE_POS;
     const int tn = (xlen - tb < QG_TILE_POS) ? xlen - tb : QG_TILE_POS;
     const bool interior = tb >= d_begin + span && tb + tn <= d_end;      // every hit of every position belongs to the item
     const uint32_t* xs = xsorted + pd.xoff + (uint64_t) tb;
-    const uint32_t tbo = (uint32_t) (tb + off);
-    const uint32_t ibase = (uint32_t) (tb - span - d_begin);             // d - d_begin = ibase + position + entry
+    const uint32_t tbo4 = (uint32_t) (tb + off) << 2;
+    const uint32_t ibase4 = (uint32_t) (tb - span - d_begin) << 2;       // 4 (d - d_begin) = ibase4 + 4 position + field
     for (int e0 = 0; e0 < tn; e0 += 4 * T) {
       uint32_t ent[4];
 #pragma unroll
-      for (int r = 0; r < 4; ++r) { const int e = e0 + r * T + tid; ent[r] = e < tn ? xs[e] : 0xFFFFFFFFu; }
+      for (int r = 0; r < 4; ++r) { const int e = e0 + r * T + tid; ent[r] = e < tn ? xs[e] : (nk << 16); }
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
-        uint32_t code = ent[r] >> 16;
-        code = code < nk ? code : nk;
-        const uint32_t pos = ent[r] & 0xFFFFu;
-        const uint32_t io = tbo + pos;
+        const uint32_t code = ent[r] >> 16, pos4 = ent[r] & 0xFFFFu;
+        const uint32_t io4 = tbo4 + pos4;
         const uint2 h = hdr[code];
-        const uint32_t len = h.y >> 24;
-        const uint32_t e_0 = h.x & 0x3FFFu, e_1 = (h.x >> 14) & 0x3FFFu, e_2 = ((h.x >> 28) | (h.y << 4)) & 0x3FFFu, e_3 = (h.y >> 10) & 0x3FFFu;
+        const uint32_t f0 = h.x & 0xFFFFu, f1 = h.x >> 16, f2 = h.y & 0xFFFFu, f3 = h.y >> 16;
+        const bool more = (f3 & 1u) && f3 != 0xFFFFu;
         if (interior) {
-          QG_RED_IF (cnt + ((io + e_0) & mask), len > 0);
-          QG_RED_IF (cnt + ((io + e_1) & mask), len > 1);
-          QG_RED_IF (cnt + ((io + e_2) & mask), len > 2);
-          QG_RED_IF (cnt + ((io + e_3) & mask), len > 3);
-          my_hits += len < 4 ? len : 4;
-          if (__any_sync (QG_FULL_MASK, len > 4)) {
-            uint32_t st = (uint32_t) bstart[code] + 4, en = len > 4 ? (uint32_t) bstart[code + 1] : 0u;
-            while (__any_sync (QG_FULL_MASK, st < en)) {
-              if (st < en) { atomicAdd (&cnt[(io + bpos[st]) & mask], 1u); ++my_hits; ++st; }
-            }
-          }
+          QG_RED_IF (cnt, (io4 + f0) & mask4, f0 != 0xFFFFu, dummy_off);
+          QG_RED_IF (cnt, (io4 + f1) & mask4, f1 != 0xFFFFu, dummy_off);
+          QG_RED_IF (cnt, (io4 + f2) & mask4, f2 != 0xFFFFu, dummy_off);
+          QG_RED_IF (cnt, (io4 + f3) & mask4, f3 != 0xFFFFu, dummy_off);
         } else {
-          const uint32_t ib = ibase + pos;
-          const bool p0 = len > 0 && ib + e_0 < dlen, p1 = len > 1 && ib + e_1 < dlen, p2 = len > 2 && ib + e_2 < dlen, p3 = len > 3 && ib + e_3 < dlen;
-          QG_RED_IF (cnt + ((io + e_0) & mask), p0);
-          QG_RED_IF (cnt + ((io + e_1) & mask), p1);
-          QG_RED_IF (cnt + ((io + e_2) & mask), p2);
-          QG_RED_IF (cnt + ((io + e_3) & mask), p3);
-          my_hits += (uint32_t) p0 + (uint32_t) p1 + (uint32_t) p2 + (uint32_t) p3;
-          if (__any_sync (QG_FULL_MASK, len > 4)) {
-            uint32_t st = (uint32_t) bstart[code] + 4, en = len > 4 ? (uint32_t) bstart[code + 1] : 0u;
-            while (__any_sync (QG_FULL_MASK, st < en)) {
-              if (st < en) { const uint32_t v = bpos[st]; if (ib + v < dlen) { atomicAdd (&cnt[(io + v) & mask], 1u); ++my_hits; } ++st; }
+          const uint32_t ib4 = ibase4 + pos4;
+          QG_RED_IF (cnt, (io4 + f0) & mask4, f0 != 0xFFFFu && ib4 + f0 < dlen4, dummy_off);
+          QG_RED_IF (cnt, (io4 + f1) & mask4, f1 != 0xFFFFu && ib4 + f1 < dlen4, dummy_off);
+          QG_RED_IF (cnt, (io4 + f2) & mask4, f2 != 0xFFFFu && ib4 + f2 < dlen4, dummy_off);
+          QG_RED_IF (cnt, (io4 + f3) & mask4, f3 != 0xFFFFu && ib4 + (f3 & ~3u) < dlen4, dummy_off);
+        }
+        if (__any_sync (QG_FULL_MASK, more)) {            // buckets longer than four: continue from the full bucket array
+          uint32_t st = 0, en = 0;
+          if (more) { st = (uint32_t) bstart[code] + 4; en = bstart[code + 1]; }
+          const uint32_t ib4 = ibase4 + pos4;
+          while (__any_sync (QG_FULL_MASK, st < en)) {
+            if (st < en) {
+              const uint32_t v4 = (uint32_t) bpos[st] << 2;
+              if (interior || ib4 + v4 < dlen4) atomicAdd (&cnt[((io4 + v4) & mask4) >> 2], 1u);
+              ++st;
             }
           }
         }
@@ -466,6 +465,7 @@ qg_seed_tile_kernel (const qg_seed_item* __restrict__ items, const qg_pair_desc*
             uint4* p4 = (uint4*) (cnt + ((uint32_t) (d0 + spo) & mask));
             const uint4 c = *p4;
             *p4 = make_uint4 (0u, 0u, 0u, 0u);
+            my_hits += c.x + c.y + c.z + c.w;
             const uint32_t cc[4] = { c.x, c.y, c.z, c.w };
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
