@@ -317,7 +317,7 @@ qg_sort_tiles_kernel (const qg_tile_job* __restrict__ jobs, const uint16_t* __re
   }
 }
 
-// One shared-memory increment at byte offset `boff` of the ring if `pred`, else on the lane's own dummy word: ptxas turns
+// One shared-memory increment at byte offset `boff` of the ring if `pred`, else on the warp's dummy word: ptxas turns
 // a PREDICATED shared atomic into a divergent branch around it (BSSY / BRA / ATOMS / BSYNC, measured: 8 instructions per
 // slot), a select between two addresses costs one.
 #define QG_RED_IF(cnt, boff, pred, dummy_off) atomicAdd ((uint32_t*) ((char*) (cnt) + ((pred) ? (boff) : (dummy_off))), 1u)
@@ -345,7 +345,7 @@ qg_seed_tile_kernel (const qg_seed_item* __restrict__ items, const qg_pair_desc*
   uint16_t* bstart = (uint16_t*) (hdr + nk + 1);
   uint16_t* bpos = bstart + ((nk + 2 + 3) & ~3u);
   uint32_t* seedmask = (uint32_t*) (bpos + ((ymax + 2 + 1) & ~1u));
-  const uint32_t dummy_off = (uint32_t) ((char*) (seedmask + QG_TSEED_ESTEP / 32 + 2) - (char*) cnt) + 4u * (threadIdx.x & 31);   // one word per lane: no bank conflict among them
+  const uint32_t dummy_off = (uint32_t) ((char*) (seedmask + QG_TSEED_ESTEP / 32 + 2) - (char*) cnt) + 4u * (threadIdx.x >> 5);   // one word per warp: ATOMS.POPC.INC folds the lanes that share an address into one access
   __shared__ uint32_t s_warp_tot[T / 32];
   __shared__ int s_open_lo, s_open_hi, s_have_open;
   __shared__ uint32_t s_nruns;
@@ -438,13 +438,12 @@ qg_seed_tile_kernel (const qg_seed_item* __restrict__ items, const qg_pair_desc*
           uint32_t st = 0, en = 0;
           if (more) { st = (uint32_t) bstart[code] + 4; en = bstart[code + 1]; }
           const uint32_t ib4 = ibase4 + pos4;
-          while (__any_sync (QG_FULL_MASK, st < en)) {
-            if (st < en) {
-              const uint32_t v4 = (uint32_t) bpos[st] << 2;
-              if (interior || ib4 + v4 < dlen4) atomicAdd (&cnt[((io4 + v4) & mask4) >> 2], 1u);
-              ++st;
-            }
-          }
+          do {
+            const bool act = st < en;
+            const uint32_t v4 = (uint32_t) bpos[act ? st : 0u] << 2;
+            QG_RED_IF (cnt, (io4 + v4) & mask4, act && (interior || ib4 + v4 < dlen4), dummy_off);
+            st += act ? 1u : 0u;
+          } while (__any_sync (QG_FULL_MASK, st < en));
         }
       }
     }
@@ -466,12 +465,15 @@ qg_seed_tile_kernel (const qg_seed_item* __restrict__ items, const qg_pair_desc*
             const uint4 c = *p4;
             *p4 = make_uint4 (0u, 0u, 0u, 0u);
             my_hits += c.x + c.y + c.z + c.w;
-            const uint32_t cc[4] = { c.x, c.y, c.z, c.w };
+            const uint32_t cxy = c.x > c.y ? c.x : c.y, czw = c.z > c.w ? c.z : c.w, cmax = cxy > czw ? cxy : czw;
+            if (COUNTS || (cmax > 0 && (int) cmax >= threshold)) {         // rare without COUNTS: some diagonal of the four is a seed
+              const uint32_t cc[4] = { c.x, c.y, c.z, c.w };
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              if (d0 + e < emit_hi) {
-                if (COUNTS) counts_out[pd.count_off + (uint64_t) (d0 + e + span)] = cc[e];     // memory-guided mode: raw counts only
-                else if ((int) cc[e] >= threshold && cc[e] > 0) nib[q] |= 1u << e;
+              for (int e = 0; e < 4; ++e) {
+                if (d0 + e < emit_hi) {
+                  if (COUNTS) counts_out[pd.count_off + (uint64_t) (d0 + e + span)] = cc[e];     // memory-guided mode: raw counts only
+                  else if ((int) cc[e] >= threshold && cc[e] > 0) nib[q] |= 1u << e;
+                }
               }
             }
           }
