@@ -635,6 +635,8 @@ def main():
             "gcups": {"viterbi_fill": vit_cups / 1e9, "cell_updates_per_read": cu_rank / iso_reads, "kmer_hits_per_read": hits_rank / iso_reads},
             "roofline": roofline,
             "cpu_baseline": cpu,
+            "timed_region": {"wall_ms": dt * 1e3, "stage_ms_summed_over_contexts": st_timed["ms_sum"],
+                             "note": "per-context CUDA-event stage times inside the timed region; their sum exceeds the wall time when the contexts' kernels overlap on the GPU"},
             "parity_checked": parity_checked, "parity_note": parity_note,
             "train": train,
         }
