@@ -75,7 +75,9 @@ __device__ __forceinline__ int qg_most_frequent (const uint8_t* __restrict__ tok
 __global__ void qg_overlap_prep_kernel (const qg_opair* __restrict__ pairs, const uint8_t* __restrict__ tok, const uint8_t* __restrict__ qual,
                                         int match_k, int gap_k, int with_qual,
                                         uint32_t* __restrict__ xa, uint32_t* __restrict__ yb, uint32_t* __restrict__ gx, uint32_t* __restrict__ gy,
-                                        const double* __restrict__ insert, double* __restrict__ ins_sums) {
+                                        const double* __restrict__ insert, double* __restrict__ ins_sums,
+                                        const double* __restrict__ match, double lrb0, double lrb1, double lrb2, double lrb3,
+                                        double* __restrict__ ea, double* __restrict__ eb) {
   __shared__ unsigned s_count[4];
   const qg_opair pd = pairs[blockIdx.x];
   const uint8_t* xt = tok + pd.xoff; const uint8_t* yt = tok + pd.yoff;
@@ -92,6 +94,12 @@ __global__ void qg_overlap_prep_kernel (const qg_opair* __restrict__ pairs, cons
     for (int t = gap_k - 1; t >= 0; --t) { const int q = i - t; gk = gk * 4 + (q >= 0 ? xt[q] : mfx); }
     XA[i] = mk * nK * Q2 + (with_qual ? xq[i] * QG_NQUAL : 0);
     GX[i + 1] = gk * nG;
+    if (ea) {                                              // on-the-fly emission (qg_overlap_fill_kernel): the x factors of qoverlap.cpp:60-66
+      double* A = ea + 5 * (pd.xa_off + i);
+      const double lrb[4] = {lrb0, lrb1, lrb2, lrb3};
+      for (int r = 0; r < 4; ++r) A[r] = lrb[r] + match[((uint64_t) r * nK + mk) * QG_NQ1 + xq[i]];
+      A[4] = insert[(mk & 3) * QG_NQ1 + xq[i]];
+    }
   }
   for (int j = threadIdx.x; j < ylen; j += blockDim.x) {
     uint32_t mk = 0, gk = 0;
@@ -106,6 +114,11 @@ __global__ void qg_overlap_prep_kernel (const qg_opair* __restrict__ pairs, cons
     }
     YB[j] = mk * Q2 + (with_qual ? yq[j] : 0);
     GY[j + 1] = gk;
+    if (eb) {
+      double* B = eb + 5 * (pd.yb_off + j);
+      for (int r = 0; r < 4; ++r) B[r] = match[((uint64_t) (pd.y_comp ? 3 - r : r) * nK + mk) * QG_NQ1 + yq[j]];
+      B[4] = insert[(mk & 3) * QG_NQ1 + yq[j]];
+    }
   }
   if (threadIdx.x == 0) {
     GX[0] = 0; GY[0] = 0;
@@ -123,6 +136,7 @@ struct qg_ofill_args {
   const uint32_t *xa, *yb, *gx, *gy;
   const double* table;               // emission table for strand 0 / 1
   const double* table1;
+  const double *ea, *eb;             // non-null: no table, the emission is evaluated per cell from 5 doubles per position of x and of y
   const double *m2m, *m2i, *m2d;     // [nG][nG]
   const double* lse;
   double effI2M, effI2I, effI2D, effD2M, effD2I, effD2D;
@@ -168,6 +182,8 @@ qg_overlap_fill_kernel (const qg_ofill_args a) {
     const int j = u - vl;
     const bool active = (j >= 1) && (j <= ylen);
     const uint32_t ybj = active ? YB[j - 1] : 0;
+    double B[5] = {0, 0, 0, 0, 0};
+    if (a.ea && active) { const double* pb = a.eb + 5 * (pd.yb_off + (uint64_t) (j - 1)); for (int r = 0; r < 5; ++r) B[r] = pb[r]; }
     const uint32_t gyj = (active && ctx_gap) ? GY[j] : 0, gyjm1 = (active && ctx_gap) ? GY[j - 1] : 0;
     unsigned long long tword = 0;
     double rM = QG_NEG_INF, rI = QG_NEG_INF, rD = QG_NEG_INF;
@@ -188,7 +204,15 @@ qg_overlap_fill_kernel (const qg_ofill_args a) {
       const bool ok = active && (s0 + c < width) && (i >= 1) && (i <= xlen);
       double E = 0, tm2m = m2m0, tm2i = m2i0, tm2d = m2d0;
       if (ok) {
-        E = table[(uint64_t) XA[i - 1] + ybj];
+        if (a.ea) {
+          // matchMinusInsert evaluated in place: the same left fold over the hidden reference base as the table entry
+          // (qoverlap.cpp:60-72), so the value has the same bits; lifts the 16^K * 94^2 table limit on K
+          const double* pa = a.ea + 5 * (pd.xa_off + (uint64_t) (i - 1));
+          double mij = QG_NEG_INF;
+#pragma unroll
+          for (int r = 0; r < 4; ++r) mij = qg_lse (a.lse, mij, pa[r] + B[r]);
+          E = (mij - pa[4]) - B[4];
+        } else E = table[(uint64_t) XA[i - 1] + ybj];
         if (ctx_gap) {
           tm2m = a.m2m[GX[i - 1] + gyjm1];                   // m2mScore(i-1, j-1)
           tm2i = a.m2i[GX[i] + gyjm1];                       // m2iScore(i,   j-1)

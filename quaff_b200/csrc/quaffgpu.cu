@@ -1744,8 +1744,10 @@ extern "C" int qg_estep (qg_ctx* ctx, const qg_dpconfig* cfg, int use_null, cons
 extern "C" int qg_set_overlap_model (qg_ctx* ctx, const qg_overlap_model* m) {
   if (ctx) cudaSetDevice (ctx->device);                    // the caller may be a host thread that never selected this context's GPU
   if (!ctx || !m) return QG_ERR_INVALID;
-  if (m->match_k < 1 || m->match_k > 2 || m->gap_k < 0 || m->gap_k > 4)
-    QG_FAIL (ctx, QG_ERR_UNSUPPORTED, "overlap model orders K=%d G=%d: this build tabulates the pair emission for K <= 2 (the table grows as 16^K * 94^2 doubles)", m->match_k, m->gap_k);
+  // K <= 2: the pair emission is tabulated (16^K * 94^2 doubles per strand); above that it is evaluated per cell from
+  // per-position factors (qg_overlap_fill_kernel, a.ea / a.eb).  G: the three [nG][nG] transition tables (24 * 16^G bytes)
+  if (m->match_k < 1 || m->match_k > 6 || m->gap_k < 0 || m->gap_k > 5)
+    QG_FAIL (ctx, QG_ERR_UNSUPPORTED, "overlap model orders K=%d G=%d outside 1..6 / 0..5", m->match_k, m->gap_k);
   qg_overlap_dev& d = ctx->omodel;
   d.match_k = m->match_k; d.gap_k = m->gap_k; d.nK = qg_pow4 (m->match_k); d.nG = qg_pow4 (m->gap_k);
   QG_TRY (qg_upload (ctx, d.d_match, m->match, sizeof (double) * 4 * d.nK * QG_NQ1));
@@ -1780,7 +1782,7 @@ extern "C" int qg_set_overlap_model (qg_ctx* ctx, const qg_overlap_model* m) {
   QG_TRY (qg_upload (ctx, d.d_m2i, m2i.data (), sizeof (double) * nG * nG));
   QG_TRY (qg_upload (ctx, d.d_m2d, m2d.data (), sizeof (double) * nG * nG));
   QG_CUDA (ctx, qg_sync (ctx));
-  d.built[0] = d.built[1] = false;
+  d.built[0] = d.built[1] = false; d.d_xonly[0].cap = d.d_xonly[1].cap = 0;
   d.set = true;
   return QG_OK;
 }
@@ -1839,10 +1841,14 @@ extern "C" int qg_overlap_viterbi (qg_ctx* ctx, const qg_dpconfig* cfg, size_t n
   const bool paths = path_out && path_offsets && coords4;
   if (path_out) *path_out = nullptr;
   const bool with_qual = Y.has_qual;
+  qg_overlap_dev& om = ctx->omodel;
+  // emission: table look-up (K <= 2, or no qualities: 16^K entries, each a 94^2-term sum) or evaluated per cell
+  const bool fly = with_qual && (om.match_k > 2 || qg_env_size ("QG_OVERLAP_FLY", 0) != 0);
+  if (!with_qual && om.match_k > 4)
+    QG_FAIL (ctx, QG_ERR_UNSUPPORTED, "overlap of reads without qualities with K=%d: the quality-marginal emission table (16^K entries of 94^2 x 4 log-sum-exp terms) is built for K <= 4", om.match_k);
   bool need[2] = {false, false};
   for (size_t p = 0; p < n_pairs; ++p) need[y_complemented[p] ? 1 : 0] = true;
-  for (int s = 0; s < 2; ++s) if (need[s]) QG_TRY (qg_overlap_ensure_table (ctx, s, with_qual));
-  qg_overlap_dev& om = ctx->omodel;
+  if (!fly) for (int s = 0; s < 2; ++s) if (need[s]) QG_TRY (qg_overlap_ensure_table (ctx, s, with_qual));
 
   qg_env_result er;
   QG_TRY (qg_envelope_stage (ctx, cfg, 24, QG_READS, n_pairs, xi, yi, er));
@@ -1884,6 +1890,7 @@ extern "C" int qg_overlap_viterbi (qg_ctx* ctx, const qg_dpconfig* cfg, size_t n
     }
     qg_dbuf &dOP = ctx->scratch[SC_RPJOBS], &dXA = ctx->scratch[SC_RP], &dYB = ctx->scratch[SC_STORE], &dGX = ctx->scratch[SC_ITEMRUNS], &dGY = ctx->scratch[SC_ITEMNRUNS];
     qg_dbuf &dINS = ctx->scratch[SC_OUT1], &dLR = ctx->scratch[SC_ENDVALS], &dLC = ctx->scratch[SC_ROWACC];
+    qg_dbuf &dEA = ctx->scratch[SC_RQ], &dEB = ctx->scratch[SC_RS];
     {
       qg_timer tm (ctx, &ctx->stats.ms_prep);
       QG_TRY (qg_upload (ctx, dOP, op.data (), sizeof (qg_opair) * np));
@@ -1892,6 +1899,7 @@ extern "C" int qg_overlap_viterbi (qg_ctx* ctx, const qg_dpconfig* cfg, size_t n
       QG_TRY (qg_reserve (ctx, dGX, sizeof (uint32_t) * (gx_tot + 1)));
       QG_TRY (qg_reserve (ctx, dGY, sizeof (uint32_t) * (gy_tot + 1)));
       QG_TRY (qg_reserve (ctx, dINS, sizeof (double) * 2 * (np + 1)));
+      if (fly) { QG_TRY (qg_reserve (ctx, dEA, sizeof (double) * 5 * (xa_tot + 1))); QG_TRY (qg_reserve (ctx, dEB, sizeof (double) * 5 * (yb_tot + 1))); }
       QG_TRY (qg_reserve (ctx, dLR, sizeof (double) * (plan.aux_slots + 1)));
       QG_TRY (qg_reserve (ctx, dLC, sizeof (double) * (plan.acc_rows + 1)));
       QG_TRY (qg_upload (ctx, ctx->scratch[SC_SEGS], plan.segs_sorted.data (), sizeof (qg_segment) * plan.segs_sorted.size ()));
@@ -1905,7 +1913,9 @@ extern "C" int qg_overlap_viterbi (qg_ctx* ctx, const qg_dpconfig* cfg, size_t n
       QG_LAUNCH (qg_overlap_prep_kernel, (unsigned) np, 256, 0, ctx->stream,
                  dOP.as<qg_opair> (), Y.d_tok.as<uint8_t> (), with_qual ? Y.d_qual.as<uint8_t> () : (const uint8_t*) nullptr,
                  om.match_k, om.gap_k, with_qual ? 1 : 0, dXA.as<uint32_t> (), dYB.as<uint32_t> (), dGX.as<uint32_t> (), dGY.as<uint32_t> (),
-                 om.d_insert.as<double> (), dINS.as<double> ());
+                 om.d_insert.as<double> (), dINS.as<double> (),
+                 om.d_match.as<double> (), om.log_ref_base[0], om.log_ref_base[1], om.log_ref_base[2], om.log_ref_base[3],
+                 fly ? dEA.as<double> () : (double*) nullptr, fly ? dEB.as<double> () : (double*) nullptr);
       QG_TRY (qg_check_launch (ctx, "qg_overlap_prep_kernel"));
       QG_LAUNCH (qg_fill_neginf_kernel, (unsigned) ((plan.acc_rows + 256) / 256), 256, 0, ctx->stream, dLC.as<double> (), plan.acc_rows + 1);
       QG_TRY (qg_check_launch (ctx, "qg_fill_neginf_kernel"));
@@ -1921,6 +1931,7 @@ extern "C" int qg_overlap_viterbi (qg_ctx* ctx, const qg_dpconfig* cfg, size_t n
       a.xa = dXA.as<uint32_t> (); a.yb = dYB.as<uint32_t> (); a.gx = dGX.as<uint32_t> (); a.gy = dGY.as<uint32_t> ();
       a.table = with_qual ? om.d_pair[0].as<double> () : om.d_none[0].as<double> ();
       a.table1 = with_qual ? om.d_pair[1].as<double> () : om.d_none[1].as<double> ();
+      if (fly) { a.table = a.table1 = nullptr; a.ea = dEA.as<double> (); a.eb = dEB.as<double> (); }
       a.m2m = om.d_m2m.as<double> (); a.m2i = om.d_m2i.as<double> (); a.m2d = om.d_m2d.as<double> ();
       a.lse = ctx->d_lse.as<double> ();
       // accessor swaps of qoverlap.h:46-51

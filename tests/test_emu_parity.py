@@ -114,6 +114,26 @@ def test_emu_overlap(emu, oracle):
     assert nf > 0
 
 
+def test_emu_overlap_emission_per_cell(emu, oracle, monkeypatch):
+    """K = 3 match contexts (G = 2): no emission table, the pair emission is evaluated per cell (qoverlap.cpp:50-75);
+    and the same path forced at K = 1, where the table path is the comparison"""
+    from quaff_b200.synth import random_ref, sample_reads
+    from quaff_b200.params import random_params
+    from quaff_b200.seqs import add_revcomps
+    ref = random_ref(420, 31)
+    reads, _, _ = sample_reads(ref, 3, 260, 32, both_strands=True)
+    seqs = add_revcomps(reads)
+    qp = random_params(np.random.default_rng(33), match_k=3, gap_k=2)
+    emu.set_reads(seqs); emu.set_overlap_params(qp)
+    r, nf = pc.check_overlap(emu, oracle, seqs, len(reads), qp, api.dp_config(kmer_threshold=5))
+    assert nf > 0
+    monkeypatch.setenv("QG_OVERLAP_FLY", "1")
+    qp = pc.default_params()
+    emu.set_overlap_params(qp)
+    r, nf = pc.check_overlap(emu, oracle, seqs, len(reads), qp, api.dp_config(kmer_threshold=5))
+    assert nf > 0
+
+
 def test_emu_probability_space_forward_backward(emu, oracle, workload):
     """the fast (default) train kernels: probability space, block-floating exponents"""
     import os

@@ -128,6 +128,23 @@ def test_overlap_order2_contexts(gpu, oracle):
     assert nf >= 3
 
 
+def test_overlap_order3_emission_per_cell(gpu, oracle, monkeypatch):
+    """K = 3, G = 2: above the table limit the pair emission is evaluated per cell from per-position factors, with the
+    fold order of qoverlap.cpp:60-72 (same bits as a table entry); the forced per-cell path at K = 2 must agree too"""
+    ref = random_ref(3000, 71)
+    reads, _, _ = sample_reads(ref, 4, 1500, 72, both_strands=True)
+    seqs = add_revcomps(reads)
+    qp = random_params(np.random.default_rng(73), match_k=3, gap_k=2)
+    gpu.set_reads(seqs); gpu.set_overlap_params(qp)
+    r, nf = pc.check_overlap(gpu, oracle, seqs, len(reads), qp, api.dp_config(kmer_threshold=10))
+    assert nf >= 3
+    monkeypatch.setenv("QG_OVERLAP_FLY", "1")
+    qp = random_params(np.random.default_rng(74), match_k=2, gap_k=1)
+    gpu.set_overlap_params(qp)
+    r, nf = pc.check_overlap(gpu, oracle, seqs, len(reads), qp, api.dp_config(kmer_threshold=10))
+    assert nf >= 3
+
+
 def test_threshold_zero_envelopes(gpu, oracle, monkeypatch):
     """-kmatchn 0: every diagonal with at least one hit is a seed, none without (diagenv.cpp:33-46) -- on the
     shared-memory kernel and on the general path"""
