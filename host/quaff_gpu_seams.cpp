@@ -2,22 +2,36 @@
 // QuaffTrainer::getCounts qmodel.cpp:2005) routed to libquaffgpu.  The reference keeps everything else: flag parsing,
 // sequence loading, params / null model, the Alignment type and every output writer.
 #include <fstream>
+#include <sstream>
 #include <algorithm>
 #include <cmath>
+#include <map>
+#include <mutex>
 #include "qmodel.h"
 #include "qoverlap.h"
 #include "quaffgpu.h"
 
 int quaffGpuDevice = -1;
+std::vector<int> quaffGpuDevices;                 // -gpu 0,1,2,3 / -gpu all: the reads shard over these devices
 
+// -gpu [device | device,device,... | all]
 bool quaffGpuParseArg (std::deque<std::string>& argvec) {
   if (argvec.size() && argvec[0] == "-gpu") {
     argvec.pop_front();
-    quaffGpuDevice = 0;
-    if (argvec.size() && !argvec[0].empty() && isdigit (argvec[0][0]) && argvec[0].size() <= 2) {
-      quaffGpuDevice = atoi (argvec[0].c_str());
+    quaffGpuDevices.clear();
+    if (argvec.size() && argvec[0] == "all") {
+      const int n = qg_device_count();
+      for (int d = 0; d < n; ++d) quaffGpuDevices.push_back (d);
+      argvec.pop_front();
+    } else if (argvec.size() && !argvec[0].empty() && argvec[0].size() <= 48
+               && argvec[0].find_first_not_of ("0123456789,") == std::string::npos && isdigit (argvec[0][0]) && isdigit (argvec[0][argvec[0].size() - 1])) {
+      std::stringstream ss (argvec[0]);
+      std::string tok;
+      while (std::getline (ss, tok, ',')) if (!tok.empty()) quaffGpuDevices.push_back (atoi (tok.c_str()));
       argvec.pop_front();
     }
+    if (quaffGpuDevices.empty()) quaffGpuDevices.push_back (0);
+    quaffGpuDevice = quaffGpuDevices[0];
     return true;
   }
   return false;
@@ -49,6 +63,19 @@ struct Gpu {
   void ok (int rc) const { Require (rc == QG_OK, "-gpu: %s", qg_last_error (ctx)); }
 };
 
+size_t envSize (const char* name, size_t dflt) { const char* v = getenv (name); return (v && *v) ? (size_t) strtoull (v, NULL, 10) : dflt; }
+
+// every device of -gpu, `perDevice` contexts on each (one host thread + one stream per context, inside the library)
+struct GpuPool {
+  qg_pool* pool;
+  GpuPool (int perDevice) : pool (NULL) {
+    if (quaffGpuDevices.empty()) quaffGpuDevices.push_back (quaffGpuDevice);
+    Require (qg_pool_create (&pool, quaffGpuDevices.data(), (int) quaffGpuDevices.size(), perDevice) == QG_OK, "-gpu: %s", qg_pool_last_error (NULL));
+  }
+  ~GpuPool () { qg_pool_destroy (pool); }
+  void ok (int rc) const { Require (rc == QG_OK, "-gpu: %s", qg_pool_last_error (pool)); }
+};
+
 qg_dpconfig gpuConfig (const QuaffDPConfig& c) {
   qg_dpconfig g;
   g.sparse = c.sparse; g.kmer_len = c.kmerLen; g.kmer_threshold = c.kmerThreshold; g.band_size = c.bandSize;
@@ -74,28 +101,31 @@ ScoreTables tables (const QuaffScores& qs) {
   return t;
 }
 
-void setAlignModel (const Gpu& g, const QuaffParams& params) {
+template<class Setter>
+void withAlignModel (const QuaffParams& params, Setter set) {
   const QuaffScores qs (params);
   const ScoreTables t = tables (qs);
   qg_align_model m;
   m.match_k = t.K; m.gap_k = t.G; m.match = t.match.data(); m.insert = t.insert.data();
   m.m2m = qs.m2m.data(); m.m2i = qs.m2i.data(); m.m2d = qs.m2d.data(); m.m2e = qs.m2e.data();
   m.d2d = qs.d2d; m.d2m = qs.d2m; m.i2i = qs.i2i; m.i2m = qs.i2m;
-  g.ok (qg_set_align_model (g.ctx, &m));
+  set (&m);
 }
+void setAlignModel (const Gpu& g, const QuaffParams& params) { withAlignModel (params, [&] (const qg_align_model* m) { g.ok (qg_set_align_model (g.ctx, m)); }); }
+void setAlignModel (const GpuPool& g, const QuaffParams& params) { withAlignModel (params, [&] (const qg_align_model* m) { g.ok (qg_pool_set_align_model (g.pool, m)); }); }
 
 // the second half of QuaffViterbiMatrix::alignment(): gapped rows, names and coordinates from the state path
 Alignment alignmentFromPath (const FastSeq& x, const FastSeq& y, uint32_t xStart, uint32_t xEnd, const uint8_t* path, uint64_t n,
                              double score, bool local) {
-  std::string xRow, yRow, yQual;
-  xRow.reserve (n); yRow.reserve (n);
+  // rows are written in place (one pass over the op path, no per-character appends)
+  const bool q = y.hasQual();
+  std::string xRow (n, Alignment::gapChar), yRow (n, Alignment::gapChar), yQual (q ? n : 0, FastSeq::maxQualityChar);
+  const char* xs = x.seq.data(); const char* ys = y.seq.data(); const char* yq = q ? y.qual.data() : NULL;
   size_t i = xStart - 1, j = 0;
   for (uint64_t t = 0; t < n; ++t) {
-    switch (path[t]) {
-    case QG_OP_MATCH:  xRow += x.seq[i++]; yRow += y.seq[j]; if (y.hasQual()) yQual += y.qual[j]; ++j; break;
-    case QG_OP_INSERT: xRow += Alignment::gapChar; yRow += y.seq[j]; if (y.hasQual()) yQual += y.qual[j]; ++j; break;
-    default:           xRow += x.seq[i++]; yRow += Alignment::gapChar; if (y.hasQual()) yQual += FastSeq::maxQualityChar; break;
-    }
+    const uint8_t op = path[t];
+    if (op != QG_OP_INSERT) xRow[t] = xs[i++];
+    if (op != QG_OP_DELETE) { yRow[t] = ys[j]; if (q) yQual[t] = yq[j]; ++j; }
   }
   Alignment align (2);
   align.gappedSeq[0].name = "Ref";
@@ -119,28 +149,75 @@ Alignment alignmentFromPath (const FastSeq& x, const FastSeq& y, uint32_t xStart
 }  // namespace
 
 // ---- seam A -------------------------------------------------------------------------------------------------------
+namespace {
+// Chunks of reads come back from the pool's worker threads in any order: each worker builds the Alignment objects of its
+// chunk and formats them (writeAlignment into a string, as the reference's own tasks do, qmodel.cpp:2796-2812) while the
+// other contexts keep the GPUs busy; chunks are then written in read order.
+struct AlignSink {
+  const QuaffAligner& aligner; std::ostream& out; const vguard<FastSeq>& x; const vguard<FastSeq>& y; bool local; size_t chunk;
+  bool toFile;                                             // -savealign: writeAlignment ignores the stream it is given; format serially
+  std::mutex mx;
+  std::map<size_t, std::string> text;
+  std::map<size_t, std::vector<Alignment> > held;
+  size_t nextFirst;
+  AlignSink (const QuaffAligner& a, std::ostream& o, const vguard<FastSeq>& x, const vguard<FastSeq>& y, bool local, size_t chunk)
+    : aligner (a), out (o), x (x), y (y), local (local), chunk (chunk), toFile (a.usingOutputFile()), nextFirst (0) { }
+  static void onChunk (void* user, int, size_t first, size_t n, const uint32_t* best, const double* score, const uint32_t* xs, const uint32_t* xe,
+                       const uint8_t* paths, const uint64_t* off) {
+    AlignSink& s = *(AlignSink*) user;
+    std::vector<Alignment> al;
+    std::ostringstream os;
+    for (size_t r = 0; r < n; ++r)
+      if (best[r] != 0xFFFFFFFFu) {
+        Alignment a = alignmentFromPath (s.x[best[r]], s.y[first + r], xs[r], xe[r], paths + off[r], off[r+1] - off[r], score[r], s.local);
+        if (s.toFile) al.push_back (a); else s.aligner.writeAlignment (os, a);
+      }
+    std::lock_guard<std::mutex> lock (s.mx);
+    if (s.toFile) s.held[first].swap (al); else s.text[first] = os.str();
+    for (;;) {                                             // flush whatever is now contiguous
+      if (s.toFile) {
+        auto it = s.held.find (s.nextFirst);
+        if (it == s.held.end()) break;
+        for (const auto& a : it->second) s.aligner.writeAlignment (s.out, a);
+        s.held.erase (it);
+      } else {
+        auto it = s.text.find (s.nextFirst);
+        if (it == s.text.end()) break;
+        s.out << it->second;
+        s.text.erase (it);
+      }
+      s.nextFirst += s.chunk;
+    }
+  }
+};
+}  // namespace
+
 void quaffGpuAlign (QuaffAligner& aligner, std::ostream& out, const vguard<FastSeq>& x, const vguard<FastSeq>& y,
                     const QuaffParams& params, const QuaffNullParams& nullModel, QuaffDPConfig& config) {
-  Gpu g;
   const Flat fx = flatten (x, false), fy = flatten (y, true);
-  g.ok (qg_set_seqs (g.ctx, QG_REFS, x.size(), fx.tok.data(), NULL, fx.off.data()));
-  g.ok (qg_set_seqs (g.ctx, QG_READS, y.size(), fy.tok.data(), fy.quals ? fy.qual.data() : NULL, fy.off.data()));
-  setAlignModel (g, params);
   const qg_dpconfig gc = gpuConfig (config);
   std::vector<double> nullLL (y.size());
   for (size_t n = 0; n < y.size(); ++n) nullLL[n] = nullModel.logLikelihood (y[n]);
-  aligner.writeAlignmentHeader (out, x, true);
   if (!aligner.printAllAlignments) {
-    std::vector<uint32_t> best (y.size()), xs (y.size()), xe (y.size());
-    std::vector<double> score (y.size());
-    std::vector<uint64_t> off (y.size() + 1);
-    uint8_t* path = NULL;
-    g.ok (qg_align_reads (g.ctx, &gc, nullLL.data(), best.data(), score.data(), xs.data(), xe.data(), &path, off.data()));
-    for (size_t n = 0; n < y.size(); ++n)
-      if (best[n] != 0xFFFFFFFFu)
-        aligner.writeAlignment (out, alignmentFromPath (x[best[n]], y[n], xs[n], xe[n], path + off[n], off[n+1] - off[n], score[n], config.local));
-    qg_free (path);
-  } else {
+    // chunks of reads over every context of every device (QUAFF_GPU_CHUNK reads each, QUAFF_GPU_CONTEXTS contexts per device)
+    const size_t chunk = std::max<size_t> (1, envSize ("QUAFF_GPU_CHUNK", 1536));
+    const size_t nChunks = (y.size() + chunk - 1) / chunk, nDev = std::max<size_t> (1, quaffGpuDevices.size());
+    const size_t perDevice = std::max<size_t> (1, std::min<size_t> (envSize ("QUAFF_GPU_CONTEXTS", 2), (nChunks + nDev - 1) / nDev));
+    GpuPool g ((int) perDevice);
+    g.ok (qg_pool_set_refs (g.pool, x.size(), fx.tok.data(), fx.off.data()));
+    setAlignModel (g, params);
+    aligner.writeAlignmentHeader (out, x, true);
+    AlignSink sink (aligner, out, x, y, config.local, chunk);
+    g.ok (qg_pool_align_reads (g.pool, &gc, y.size(), fy.tok.data(), fy.quals ? fy.qual.data() : NULL, fy.off.data(), nullLL.data(), chunk,
+                               AlignSink::onChunk, &sink));
+    return;
+  }
+  Gpu g;
+  g.ok (qg_set_seqs (g.ctx, QG_REFS, x.size(), fx.tok.data(), NULL, fx.off.data()));
+  g.ok (qg_set_seqs (g.ctx, QG_READS, y.size(), fy.tok.data(), fy.quals ? fy.qual.data() : NULL, fy.off.data()));
+  setAlignModel (g, params);
+  aligner.writeAlignmentHeader (out, x, true);
+  {
     // -printall: every reference with a finite score, best first, earlier reference first on ties (multiset order)
     const size_t nx = x.size(), np = nx * y.size();
     std::vector<uint32_t> xi (np), yi (np), xs (np), xe (np);
@@ -227,13 +304,13 @@ void quaffGpuOverlap (QuaffOverlapAligner& aligner, std::ostream& out, const vgu
 QuaffParamCounts quaffGpuGetCounts (QuaffTrainer& trainer, const vguard<FastSeq>& x, const vguard<FastSeq>& y,
                                     const QuaffParams& params, const QuaffNullParams& nullModel, QuaffDPConfig& config,
                                     vguard<vguard<size_t> >& sortOrder, double& logLike) {
-  Gpu g;
+  // one context per device; the reads split into contiguous ranges, the partial counts are summed by the library
+  GpuPool g (1);
   const Flat fx = flatten (x, false), fy = flatten (y, true);
   Require (fy.quals, "Forward-Backward algorithm requires quality scores to fit model");
-  g.ok (qg_set_seqs (g.ctx, QG_REFS, x.size(), fx.tok.data(), NULL, fx.off.data()));
-  g.ok (qg_set_seqs (g.ctx, QG_READS, y.size(), fy.tok.data(), fy.qual.data(), fy.off.data()));
+  g.ok (qg_pool_set_refs (g.pool, x.size(), fx.tok.data(), fx.off.data()));
   setAlignModel (g, params);
-  if (getenv ("QUAFF_GPU_EXACT")) g.ok (qg_set_option (g.ctx, QG_OPT_FB_EXACT, 1));
+  if (getenv ("QUAFF_GPU_EXACT")) g.ok (qg_pool_set_option (g.pool, QG_OPT_FB_EXACT, 1));
   const qg_dpconfig gc = gpuConfig (config);
   const size_t nx = x.size(), ny = y.size();
   std::vector<double> nullLL (ny), yLL (ny);
@@ -245,7 +322,8 @@ QuaffParamCounts quaffGpuGetCounts (QuaffTrainer& trainer, const vguard<FastSeq>
   }
   const unsigned int K = params.matchContext.kmerLen, G = params.indelContext.kmerLen;
   std::vector<double> flat (qg_counts_size (K, G));
-  g.ok (qg_estep (g.ctx, &gc, trainer.allowNullModel ? 1 : 0, nullLL.data(), so.data(), soLen.data(), yLL.data(), flat.data(), &logLike));
+  g.ok (qg_pool_estep (g.pool, &gc, trainer.allowNullModel ? 1 : 0, nx, ny, fy.tok.data(), fy.qual.data(), fy.off.data(), nullLL.data(),
+                       so.data(), soLen.data(), yLL.data(), flat.data(), &logLike));
   for (size_t n = 0; n < ny; ++n) sortOrder[n] = vguard<size_t> (so.begin() + n * nx, so.begin() + n * nx + soLen[n]);
   QuaffParamCounts counts (K, G);
   size_t k = 0;

@@ -194,6 +194,37 @@ int qg_overlap_reads (qg_ctx* ctx, const qg_dpconfig* cfg, size_t n_originals, c
                       size_t* n_pairs_out, uint32_t** xi_out, uint32_t** yi_out,
                       double** score_out, uint32_t** coords4_out, uint8_t** path_out, uint64_t** path_offsets_out);
 
+/* ---- several contexts / several GPUs behind one handle ------------------------- */
+/* One process drives every device: the reads shard over `contexts_per_device` contexts on each of `devices`
+ * (one host thread + one stream each); every context holds the reference set and the model.  This is what
+ * `quaff ... -gpu 0,1,2,3` / `-gpu all` binds (host/quaff_gpu_seams.cpp); it replaces the reference's thread pool
+ * (qmodel.cpp:2650-2668 for align, qmodel.cpp:2013-2029 for the E-step).                                  */
+typedef struct qg_pool qg_pool;
+int  qg_device_count (void);
+int  qg_pool_create (qg_pool** out, const int* devices, int n_devices, int contexts_per_device);
+void qg_pool_destroy (qg_pool* pool);
+const char* qg_pool_last_error (const qg_pool* pool);     /* pool may be NULL: last qg_pool_create failure */
+int  qg_pool_size (const qg_pool* pool);                  /* number of contexts                             */
+qg_ctx* qg_pool_context (qg_pool* pool, int i);           /* for qg_get_stats                               */
+int  qg_pool_set_refs (qg_pool* pool, size_t n, const uint8_t* tok, const uint64_t* offsets);
+int  qg_pool_set_align_model (qg_pool* pool, const qg_align_model* model);
+int  qg_pool_set_option (qg_pool* pool, int option, int64_t value);
+/* seam A over a whole read set held in HOST memory: chunks of `chunk_reads` reads (0 = default) go to the contexts as
+ * they become free; `on_chunk` is called once per chunk, on the worker's thread (concurrently with other chunks, in
+ * no particular order), with the outputs of qg_align_reads for reads [first_read, first_read + n_reads); the buffers
+ * are valid during the call only.                                                                      */
+typedef void (*qg_chunk_fn) (void* user, int worker, size_t first_read, size_t n_reads,
+                             const uint32_t* best_ref, const double* score, const uint32_t* x_start, const uint32_t* x_end,
+                             const uint8_t* paths, const uint64_t* path_offsets /* n_reads+1, relative to paths */);
+int  qg_pool_align_reads (qg_pool* pool, const qg_dpconfig* cfg, size_t n_reads, const uint8_t* tok, const uint8_t* qual,
+                          const uint64_t* offsets, const double* null_loglike, size_t chunk_reads,
+                          qg_chunk_fn on_chunk, void* user);
+/* seam C over a whole read set: contiguous read ranges per context, the partial counts and log-likelihoods summed on
+ * the host in context order.  Arguments as qg_estep, for all n_reads reads (sort_order is [n_reads][n_refs]).      */
+int  qg_pool_estep (qg_pool* pool, const qg_dpconfig* cfg, int use_null, size_t n_refs, size_t n_reads,
+                    const uint8_t* tok, const uint8_t* qual, const uint64_t* offsets, const double* null_loglike,
+                    uint32_t* sort_order, uint32_t* sort_len, double* y_loglike, double* param_counts, double* loglike_sum);
+
 /* ---- instrumentation ------------------------------------------------------------------------------ */
 typedef struct {
   double ms_seed, ms_envelope, ms_prep, ms_viterbi, ms_traceback, ms_forward, ms_backward, ms_overlap, ms_h2d, ms_d2h;

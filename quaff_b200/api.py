@@ -34,6 +34,8 @@ ABI_SYMBOLS = [
     "qg_set_align_model", "qg_scores_from_params", "qg_null_loglike", "qg_envelopes", "qg_viterbi", "qg_forward",
     "qg_backward_counts", "qg_align_reads", "qg_align_reads_range", "qg_estep", "qg_set_overlap_model", "qg_overlap_viterbi", "qg_overlap_rows",
     "qg_overlap_reads", "qg_get_stats",
+    "qg_device_count", "qg_pool_create", "qg_pool_destroy", "qg_pool_last_error", "qg_pool_size", "qg_pool_context", "qg_pool_set_refs",
+    "qg_pool_set_align_model", "qg_pool_set_option", "qg_pool_align_reads", "qg_pool_estep",
 ]
 
 
@@ -117,6 +119,13 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     L.qg_free.argtypes = [C.c_void_p]
     L.qg_destroy.argtypes = [C.c_void_p]
     L.qg_create.argtypes = [C.POINTER(C.c_void_p), C.c_int]
+    L.qg_pool_last_error.restype = C.c_char_p
+    L.qg_pool_last_error.argtypes = [C.c_void_p]
+    L.qg_pool_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.c_int, C.c_int]
+    L.qg_pool_destroy.argtypes = [C.c_void_p]
+    L.qg_pool_context.restype = C.c_void_p
+    L.qg_pool_context.argtypes = [C.c_void_p, C.c_int]
+    L.qg_pool_size.argtypes = [C.c_void_p]
     return L
 
 
@@ -513,3 +522,108 @@ class QuaffGPUPool:
 
     def stats(self, reset: bool = False) -> List[dict]:
         return [g.stats(reset) for g in self.ctxs]
+
+
+CHUNK_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_size_t, C.c_size_t, c_u32_p, c_double_p, c_u32_p, c_u32_p, c_u8_p, c_u64_p)
+
+
+class QuaffPool:
+    """The native multi-context / multi-GPU handle (include/quaffgpu.h, qg_pool_*): one process drives every device; host
+    threads, chunking and the E-step count sum live in the library.  `quaff ... -gpu 0,1,..` binds the same calls."""
+
+    def __init__(self, devices: Sequence[int] = (0,), contexts_per_device: int = 2, lib_path: Optional[str] = None):
+        self.L = load_library(lib_path)
+        self.pool = C.c_void_p()
+        dev = (C.c_int * len(devices))(*[int(d) for d in devices])
+        rc = self.L.qg_pool_create(C.byref(self.pool), dev, len(devices), int(contexts_per_device))
+        if rc != 0:
+            raise QuaffGpuError(rc, (self.L.qg_pool_last_error(None) or b"").decode())
+        self.n_refs = 0
+        self.match_k, self.gap_k = 1, 0
+
+    def close(self):
+        if self.pool:
+            self.L.qg_pool_destroy(self.pool)
+            self.pool = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise QuaffGpuError(rc, (self.L.qg_pool_last_error(self.pool) or b"").decode())
+
+    def size(self) -> int:
+        return int(self.L.qg_pool_size(self.pool))
+
+    def set_refs(self, refs: Sequence[FastSeq]):
+        tok, _, off = _flatten(refs, False)
+        self._check(self.L.qg_pool_set_refs(self.pool, C.c_size_t(len(refs)), tok.ctypes.data_as(c_u8_p), off.ctypes.data_as(c_u64_p)))
+        self.n_refs = len(refs)
+
+    def set_params(self, qp: QuaffParams):
+        s = scores_from_params(qp, self.L)
+        self._keep = s
+        m = _AlignModel(s.match_k, s.gap_k, _dp(np.ascontiguousarray(s.match)), _dp(np.ascontiguousarray(s.insert)),
+                        _dp(s.m2m), _dp(s.m2i), _dp(s.m2d), _dp(s.m2e), s.d2d, s.d2m, s.i2i, s.i2m)
+        self._check(self.L.qg_pool_set_align_model(self.pool, C.byref(m)))
+        self.match_k, self.gap_k = s.match_k, s.gap_k
+
+    def set_fb_exact(self, exact: bool):
+        self._check(self.L.qg_pool_set_option(self.pool, 1, C.c_int64(1 if exact else 0)))
+
+    def align_reads_raw(self, cfg: DPConfig, tok: np.ndarray, qual: Optional[np.ndarray], off: np.ndarray, null_ll: np.ndarray, chunk_reads: int = 0):
+        """seam A over host buffers; returns per-read arrays and the concatenated op paths in read order"""
+        n = len(off) - 1
+        null_ll = np.ascontiguousarray(null_ll, dtype=np.float64)
+        best = np.zeros(n, np.uint32); score = np.zeros(n); xs = np.zeros(n, np.uint32); xe = np.zeros(n, np.uint32)
+        plen = np.zeros(n + 1, np.uint64)
+        chunks = {}
+
+        def on_chunk(user, worker, first, cnt, b, sc, x0, x1, paths, poff):
+            first, cnt = int(first), int(cnt)
+            best[first:first + cnt] = np.ctypeslib.as_array(b, shape=(cnt,))
+            score[first:first + cnt] = np.ctypeslib.as_array(sc, shape=(cnt,))
+            xs[first:first + cnt] = np.ctypeslib.as_array(x0, shape=(cnt,))
+            xe[first:first + cnt] = np.ctypeslib.as_array(x1, shape=(cnt,))
+            o = np.ctypeslib.as_array(poff, shape=(cnt + 1,))
+            plen[first + 1:first + cnt + 1] = np.diff(o)
+            total = int(o[cnt])
+            chunks[first] = np.ctypeslib.as_array(paths, shape=(max(total, 1),))[:total].copy() if total else np.zeros(0, np.uint8)
+        cb = CHUNK_FN(on_chunk)
+        self._check(self.L.qg_pool_align_reads(self.pool, C.byref(cfg), C.c_size_t(n), tok.ctypes.data_as(c_u8_p),
+                                               qual.ctypes.data_as(c_u8_p) if qual is not None else None, off.ctypes.data_as(c_u64_p),
+                                               _dp(null_ll), C.c_size_t(chunk_reads), cb, None))
+        paths = np.concatenate([chunks[k] for k in sorted(chunks)]) if chunks else np.zeros(0, np.uint8)
+        return dict(best_ref=best, score=score, x_start=xs, x_end=xe, paths=paths, path_offsets=np.cumsum(plen).astype(np.uint64))
+
+    def align_reads(self, cfg: DPConfig, reads: Sequence[FastSeq], null_ll: np.ndarray, chunk_reads: int = 0, use_quals: bool = True):
+        want = use_quals and len(reads) > 0 and all(r.has_qual() for r in reads)
+        tok, qual, off = _flatten(reads, want)
+        return self.align_reads_raw(cfg, tok, qual, off, null_ll, chunk_reads)
+
+    def estep(self, cfg: DPConfig, use_null: bool, reads: Sequence[FastSeq], null_ll: np.ndarray, sort_order: Optional[List[List[int]]] = None):
+        ny, nx = len(reads), self.n_refs
+        tok, qual, off = _flatten(reads, True)
+        so = np.zeros((ny, nx), dtype=np.uint32); sl = np.zeros(ny, dtype=np.uint32)
+        for m in range(ny):
+            o = list(range(nx)) if sort_order is None else sort_order[m]
+            so[m, :len(o)] = o; sl[m] = len(o)
+        null_ll = np.ascontiguousarray(null_ll, dtype=np.float64)
+        nc = int(self.L.qg_counts_size(self.match_k, self.gap_k))
+        yll = np.zeros(ny); counts = np.zeros(nc); tot = C.c_double()
+        self._check(self.L.qg_pool_estep(self.pool, C.byref(cfg), int(use_null), C.c_size_t(nx), C.c_size_t(ny), tok.ctypes.data_as(c_u8_p),
+                                         qual.ctypes.data_as(c_u8_p), off.ctypes.data_as(c_u64_p), _dp(null_ll), so.ctypes.data_as(c_u32_p),
+                                         sl.ctypes.data_as(c_u32_p), _dp(yll), _dp(counts), C.byref(tot)))
+        return dict(y_loglike=yll, counts=counts, loglike=tot.value, sort_order=[list(map(int, so[m, :sl[m]])) for m in range(ny)])
+
+    def stats(self, reset: bool = False) -> List[dict]:
+        out = []
+        for i in range(self.size()):
+            st = Stats()
+            self.L.qg_get_stats(C.c_void_p(self.L.qg_pool_context(self.pool, i)), C.byref(st), 1 if reset else 0)
+            out.append(st.as_dict())
+        return out

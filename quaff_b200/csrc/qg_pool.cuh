@@ -1,0 +1,151 @@
+// Several contexts on one or more devices behind ONE handle: the multi-GPU form of the three seams.
+// Reads shard over the contexts (the reference's tasks are independent per read: QuaffAlignmentTask, qmodel.cpp:2575-2622;
+// QuaffCountingTask, qmodel.cpp:1879-1960); every context holds the reference set, its tile index and the model.
+//   align : the read set is cut into chunks; each context's host thread takes the next chunk when it is free (dynamic
+//           balance, as the reference's thread pool does, qmodel.cpp:2650-2668), and hands the finished chunk to the
+//           caller's callback ON THAT THREAD, so that output formatting runs in parallel with the other contexts' GPU work
+//   E-step: contiguous read ranges, one per context; the partial QuaffParamCounts are summed in context order on the host
+//           (a single process owns all devices here: the sum of <= 24 509 doubles needs no collective; with one process
+//           per GPU the caller all-reduces instead, quaff_b200/dist.py)
+#ifndef QG_POOL_CUH
+#define QG_POOL_CUH
+#include <thread>
+#include <atomic>
+#include <mutex>
+
+struct qg_pool {
+  std::vector<qg_ctx*> ctx;
+  std::vector<int> device;
+  std::string err;
+  int K = 1, G = 0;
+};
+
+static thread_local std::string qg_pool_create_error;
+
+extern "C" int qg_device_count (void) {
+  int n = 0;
+  if (cudaGetDeviceCount (&n) != cudaSuccess) { cudaGetLastError (); return 0; }
+  return n;
+}
+
+extern "C" int qg_pool_create (qg_pool** out, const int* devices, int n_devices, int contexts_per_device) {
+  if (!out || n_devices < 1 || contexts_per_device < 1 || !devices) return QG_ERR_INVALID;
+  *out = nullptr;
+  qg_pool* p = new qg_pool;
+  for (int c = 0; c < contexts_per_device; ++c)              // context order: device-major inside every round, so that
+    for (int d = 0; d < n_devices; ++d) {                      // the first n_devices workers sit on different devices
+      qg_ctx* x = nullptr;
+      const int rc = qg_create (&x, devices[d]);
+      if (rc != QG_OK) {
+        qg_pool_create_error = qg_last_error (nullptr);
+        for (qg_ctx* y : p->ctx) qg_destroy (y);
+        delete p;
+        return rc;
+      }
+      p->ctx.push_back (x); p->device.push_back (devices[d]);
+    }
+  *out = p;
+  return QG_OK;
+}
+
+extern "C" void qg_pool_destroy (qg_pool* p) {
+  if (!p) return;
+  for (qg_ctx* x : p->ctx) qg_destroy (x);
+  delete p;
+}
+
+extern "C" const char* qg_pool_last_error (const qg_pool* p) { return p ? p->err.c_str () : qg_pool_create_error.c_str (); }
+extern "C" int qg_pool_size (const qg_pool* p) { return p ? (int) p->ctx.size () : 0; }
+extern "C" qg_ctx* qg_pool_context (qg_pool* p, int i) { return (p && i >= 0 && i < (int) p->ctx.size ()) ? p->ctx[i] : nullptr; }
+
+// run fn (worker) on one host thread per context; first error wins
+template<class F>
+static int qg_pool_run (qg_pool* p, F fn) {
+  const int n = (int) p->ctx.size ();
+  std::vector<int> rc (n, QG_OK);
+  std::vector<std::thread> th;
+  for (int w = 1; w < n; ++w) th.emplace_back ([&, w] { rc[w] = fn (w); });
+  rc[0] = fn (0);
+  for (auto& t : th) t.join ();
+  for (int w = 0; w < n; ++w)
+    if (rc[w] != QG_OK) { p->err = std::string ("context ") + std::to_string (w) + " (device " + std::to_string (p->device[w]) + "): " + qg_last_error (p->ctx[w]); return rc[w]; }
+  return QG_OK;
+}
+
+extern "C" int qg_pool_set_refs (qg_pool* p, size_t n, const uint8_t* tok, const uint64_t* offsets) {
+  if (!p) return QG_ERR_INVALID;
+  return qg_pool_run (p, [&] (int w) { return qg_set_seqs (p->ctx[w], QG_REFS, n, tok, nullptr, offsets); });
+}
+
+extern "C" int qg_pool_set_align_model (qg_pool* p, const qg_align_model* m) {
+  if (!p || !m) return QG_ERR_INVALID;
+  p->K = m->match_k; p->G = m->gap_k;
+  return qg_pool_run (p, [&] (int w) { return qg_set_align_model (p->ctx[w], m); });
+}
+
+extern "C" int qg_pool_set_option (qg_pool* p, int option, int64_t value) {
+  if (!p) return QG_ERR_INVALID;
+  for (qg_ctx* x : p->ctx) { const int rc = qg_set_option (x, option, value); if (rc != QG_OK) { p->err = qg_last_error (x); return rc; } }
+  return QG_OK;
+}
+
+extern "C" int qg_pool_align_reads (qg_pool* p, const qg_dpconfig* cfg, size_t n_reads, const uint8_t* tok, const uint8_t* qual,
+                                    const uint64_t* offsets, const double* null_loglike, size_t chunk_reads,
+                                    qg_chunk_fn on_chunk, void* user) {
+  if (!p || !cfg || !offsets || !null_loglike || !on_chunk || (n_reads && !tok)) return QG_ERR_INVALID;
+  if (chunk_reads == 0) chunk_reads = 1536;
+  const size_t n_chunks = (n_reads + chunk_reads - 1) / chunk_reads;
+  std::atomic<size_t> next (0);
+  std::atomic<int> failed (0);
+  return qg_pool_run (p, [&] (int w) -> int {
+    qg_ctx* ctx = p->ctx[w];
+    std::vector<uint64_t> off, poff;
+    std::vector<uint32_t> best, xs, xe;
+    std::vector<double> score;
+    for (;;) {
+      const size_t c = next.fetch_add (1);
+      if (c >= n_chunks || failed.load ()) return QG_OK;
+      const size_t r0 = c * chunk_reads, r1 = std::min (n_reads, r0 + chunk_reads), nr = r1 - r0;
+      off.resize (nr + 1);
+      for (size_t r = 0; r <= nr; ++r) off[r] = offsets[r0 + r] - offsets[r0];
+      int rc = qg_set_seqs (ctx, QG_READS, nr, tok + offsets[r0], qual ? qual + offsets[r0] : nullptr, off.data ());
+      if (rc != QG_OK) { failed = 1; return rc; }
+      best.resize (nr); xs.resize (nr); xe.resize (nr); score.resize (nr); poff.resize (nr + 1);
+      uint8_t* path = nullptr;
+      rc = qg_align_reads (ctx, cfg, null_loglike + r0, best.data (), score.data (), xs.data (), xe.data (), &path, poff.data ());
+      if (rc != QG_OK) { failed = 1; return rc; }
+      on_chunk (user, w, r0, nr, best.data (), score.data (), xs.data (), xe.data (), path, poff.data ());
+      qg_free (path);
+    }
+  });
+}
+
+extern "C" int qg_pool_estep (qg_pool* p, const qg_dpconfig* cfg, int use_null, size_t n_refs, size_t n_reads, const uint8_t* tok, const uint8_t* qual,
+                              const uint64_t* offsets, const double* null_loglike, uint32_t* sort_order, uint32_t* sort_len,
+                              double* y_loglike, double* param_counts, double* loglike_sum) {
+  if (!p || !cfg || !offsets || !sort_order || !sort_len || !y_loglike || !param_counts || !loglike_sum || (n_reads && (!tok || !qual))) return QG_ERR_INVALID;
+  const int n = (int) p->ctx.size ();
+  const size_t nc = qg_counts_size (p->K, p->G);
+  std::vector<std::vector<double>> part (n, std::vector<double> (nc, 0.0));
+  std::vector<double> ll (n, 0.0);
+  // contiguous ranges balanced by bases (the DP work of a read is proportional to its length)
+  std::vector<size_t> cut (n + 1, n_reads);
+  cut[0] = 0;
+  { const uint64_t total = offsets[n_reads] - offsets[0]; size_t r = 0;
+    for (int w = 1; w < n; ++w) { const uint64_t want = offsets[0] + total * (uint64_t) w / (uint64_t) n; while (r < n_reads && offsets[r] < want) ++r; cut[w] = r; } }
+  const int rc = qg_pool_run (p, [&] (int w) -> int {
+    const size_t r0 = cut[w], r1 = cut[w + 1], nr = r1 - r0;
+    if (!nr) return QG_OK;
+    qg_ctx* ctx = p->ctx[w];
+    std::vector<uint64_t> off (nr + 1);
+    for (size_t r = 0; r <= nr; ++r) off[r] = offsets[r0 + r] - offsets[r0];
+    QG_TRY (qg_set_seqs (ctx, QG_READS, nr, tok + offsets[r0], qual + offsets[r0], off.data ()));
+    return qg_estep (ctx, cfg, use_null, null_loglike ? null_loglike + r0 : nullptr, sort_order + r0 * n_refs, sort_len + r0, y_loglike + r0, part[w].data (), &ll[w]);
+  });
+  if (rc != QG_OK) return rc;
+  for (size_t k = 0; k < nc; ++k) { double s = 0; for (int w = 0; w < n; ++w) s += part[w][k]; param_counts[k] = s; }
+  double s = 0; for (int w = 0; w < n; ++w) s += ll[w];
+  *loglike_sum = s;
+  return QG_OK;
+}
+#endif

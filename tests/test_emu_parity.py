@@ -229,3 +229,32 @@ def test_emu_pool_with_more_contexts_than_reads(emu_lib, oracle):
         assert np.array_equal(np.concatenate(one["paths"]) if isinstance(one["paths"], list) else one["paths"], b["paths"])
     finally:
         P.close()
+
+
+def test_emu_pool_matches_single_context(emu, emu_lib, oracle):
+    """qg_pool_*: chunks of reads over two contexts (host threads inside the library), results in read order; E-step count
+    sum over contiguous read ranges -- both against the single-context entry points"""
+    from quaff_b200.params import QuaffNullParams
+    import os
+    x, reads = pc.make_workload(ref_len=3000, n_reads=5, read_len=220, seed=13)
+    qp = pc.default_params()
+    nullp = QuaffNullParams.load(os.path.join(os.path.dirname(__file__), "golden", "testquaffnullparams.json"))
+    cfg = api.dp_config(kmer_threshold=6)
+    null_ll = np.array([api.null_loglike(nullp, r, emu.L) for r in reads])
+    emu.set_refs(x); emu.set_reads(reads); emu.set_params(qp)
+    one = emu.align_reads(cfg, null_ll, split_paths=False)
+    P = api.QuaffPool(devices=[0], contexts_per_device=2, lib_path=emu_lib)
+    try:
+        assert P.size() == 2
+        P.set_refs(x); P.set_params(qp)
+        many = P.align_reads(cfg, reads, null_ll, chunk_reads=2)          # 3 chunks over 2 contexts
+        for k in ("best_ref", "score", "x_start", "x_end", "paths", "path_offsets"):
+            assert np.array_equal(np.asarray(one[k]), np.asarray(many[k])), k
+        emu.set_fb_exact(True); P.set_fb_exact(True)
+        e1 = emu.estep(cfg, True, null_ll)
+        e2 = P.estep(cfg, True, reads, null_ll)
+        assert e1["sort_order"] == e2["sort_order"] and np.array_equal(e1["y_loglike"], e2["y_loglike"])
+        np.testing.assert_allclose(e2["counts"], e1["counts"], rtol=1e-12, atol=1e-300)
+        assert abs(e1["loglike"] - e2["loglike"]) <= 1e-12 * abs(e1["loglike"])
+    finally:
+        P.close()
