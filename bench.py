@@ -31,7 +31,7 @@ sys.path.insert(0, ROOT)
 
 REF_LEN = 5_000_000
 READ_LEN = 8000
-READS_PER_STEP = 1536            # per GPU; ~4.3 GB of traceback pointers per step
+READS_PER_STEP = 6144            # per GPU: 1536 per context x 4 contexts (Viterbi and traceback launches of 1536 reads fill the SMs, 768 did not); ~22 GB of traceback pointers per step
 CFG4_WORKLOAD = ("cfg4: quaff align, synthetic 8 kb nanopore-like reads (12% error) vs 5 Mb random reference, both strands, "
                  "-kmatch 6 -kmatchn 20 -kmatchband 64, default params, fixed null model")
 POOL_BATCHES = 2                 # distinct read batches cycled through the steps (bounds host synthesis time)

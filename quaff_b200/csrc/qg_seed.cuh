@@ -279,12 +279,10 @@ qg_seed_kernel (const qg_seed_item* __restrict__ items, const qg_pair_desc* __re
 #define QG_TILE_POS 1024
 #define QG_TSEED_RING 4096u
 #define QG_TSEED_THREADS 128
-#define QG_TSEED_QCAP 16u            /* tiny: the overflow path (inline tail walk) is exercised too */
 #else
 #define QG_TILE_POS 16384
 #define QG_TSEED_RING 32768u
 #define QG_TSEED_THREADS 1024
-#define QG_TSEED_QCAP 4096u          /* deferred long-bucket positions per tile (16 KB) */
 #endif
 #define QG_TSEED_ESTEP (QG_TSEED_THREADS * 8)      // diagonals one pass of the emit scan covers
 
@@ -321,14 +319,11 @@ qg_sort_tiles_kernel (const qg_tile_job* __restrict__ jobs, const uint16_t* __re
 
 // One shared-memory increment at byte offset `boff` of the ring if `pred`, else on the warp's dummy word: ptxas turns
 // a PREDICATED shared atomic into a divergent branch around it (BSSY / BRA / ATOMS / BSYNC, measured: 8 instructions per
-// slot), a select between two addresses costs one.
+// slot), a select between two addresses costs one.  (A reduction predicated at the PTX level -- "@p red.shared.add" -- is
+// turned into the same branch by ptxas 12.9.)
 #define QG_RED_IF(cnt, boff, pred, dummy_off) atomicAdd ((uint32_t*) ((char*) (cnt) + ((pred) ? (boff) : (dummy_off))), 1u)
 
-// shared memory: cnt[QG_TSEED_RING] u32 | hdr[nk + 1] uint2 | bstart[nk + 2] u16 | bpos[ymax + 2] u16 | seedmask[ESTEP/32 + 2] u32 | dummy[32] u32 | queue[QCAP] u32
-//   queue      = the tile's positions whose bucket has more than four entries (4.8 % at 8 kb): pushed by the position loop
-//                (one ballot + one counter increment per warp), drained after it with every lane on a tail.  Walking the
-//                tails inside the position loop kept whole warps in a loop for the one or two lanes that needed it:
-//                45 % of the kernel's instructions for 3.5 % of its hits (ncu r02 seed_c)
+// shared memory: cnt[QG_TSEED_RING] u32 | hdr[nk + 1] uint2 | bstart[nk + 2] u16 | bpos[ymax + 2] u16 | seedmask[ESTEP/32 + 2] u32 | dummy[32] u32
 //   hdr[code]  = the first four bucket entries as 16-bit fields holding 4 * (span - j), the byte offset a hit adds to the ring
 //                address; 0xFFFF = empty slot; bit 0 of field 3 = "the bucket has more than four entries"; hdr[nk] = all empty
 //                (positions without a k-mer)
@@ -352,9 +347,7 @@ qg_seed_tile_kernel (const qg_seed_item* __restrict__ items, const qg_pair_desc*
   uint16_t* bpos = bstart + ((nk + 2 + 3) & ~3u);
   uint32_t* seedmask = (uint32_t*) (bpos + ((ymax + 2 + 1) & ~1u));
   const uint32_t dummy_off = (uint32_t) ((char*) (seedmask + QG_TSEED_ESTEP / 32 + 2) - (char*) cnt) + 4u * (threadIdx.x >> 5);   // one word per warp: ATOMS.POPC.INC folds the lanes that share an address into one access
-  uint32_t* queue = seedmask + QG_TSEED_ESTEP / 32 + 2 + 32;
   __shared__ uint32_t s_warp_tot[T / 32];
-  __shared__ uint32_t s_qn[2];                            // by tile parity: the drain of one tile resets the next tile's counter
   __shared__ int s_open_lo, s_open_hi, s_have_open;
   __shared__ uint32_t s_nruns;
 
@@ -367,7 +360,7 @@ qg_seed_tile_kernel (const qg_seed_item* __restrict__ items, const qg_pair_desc*
 
   // -- 1. bucket index of the read (counting sort of its k-mer starts by code)
   for (uint32_t c = tid; c < ring; c += T) cnt[c] = 0;
-  if (tid == 0) { s_have_open = 0; s_nruns = 0; s_open_lo = 0; s_open_hi = 0; s_qn[0] = 0; s_qn[1] = 0; }
+  if (tid == 0) { s_have_open = 0; s_nruns = 0; s_open_lo = 0; s_open_hi = 0; }
   __syncthreads ();
   for (int j = tid; j < nyk; j += T) atomicAdd (&cnt[yc[j]], 1u);
   __syncthreads ();
@@ -419,10 +412,17 @@ qg_seed_tile_kernel (const qg_seed_item* __restrict__ items, const qg_pair_desc*
     const uint32_t* xs = xsorted + pd.xoff + (uint64_t) tb;
     const uint32_t tbo4 = (uint32_t) (tb + off) << 2;
     const uint32_t ibase4 = (uint32_t) (tb - span - d_begin) << 2;       // 4 (d - d_begin) = ibase4 + 4 position + field
+    const bool whole = tn == QG_TILE_POS;                                // QG_TILE_POS is a multiple of 4 T: no bounds tests
     for (int e0 = 0; e0 < tn; e0 += 4 * T) {
       uint32_t ent[4];
+      if (whole) {
+        const uint32_t* xe = xs + e0 + tid;
 #pragma unroll
-      for (int r = 0; r < 4; ++r) { const int e = e0 + r * T + tid; ent[r] = e < tn ? xs[e] : (nk << 16); }
+        for (int r = 0; r < 4; ++r) ent[r] = xe[r * T];
+      } else {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) { const int e = e0 + r * T + tid; ent[r] = e < tn ? xs[e] : (nk << 16); }
+      }
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
         const uint32_t code = ent[r] >> 16, pos4 = ent[r] & 0xFFFFu;
@@ -442,42 +442,16 @@ qg_seed_tile_kernel (const qg_seed_item* __restrict__ items, const qg_pair_desc*
           QG_RED_IF (cnt, (io4 + f2) & mask4, f2 != 0xFFFFu && ib4 + f2 < dlen4, dummy_off);
           QG_RED_IF (cnt, (io4 + f3) & mask4, f3 != 0xFFFFu && ib4 + (f3 & ~3u) < dlen4, dummy_off);
         }
-        const uint32_t mm = __ballot_sync (QG_FULL_MASK, more);
-        if (mm) {                                         // buckets longer than four: the rest of the bucket is walked after the position loop
-          uint32_t qb = 0;
-          if (lane == 0) qb = atomicAdd (&s_qn[tile & 1], (uint32_t) __popc (mm));
-          qb = __shfl_sync (QG_FULL_MASK, qb, 0);
-          const uint32_t slot = qb + (uint32_t) __popc (mm & ((1u << lane) - 1u));
-          if (more) {
-            if (slot < QG_TSEED_QCAP) queue[slot] = ent[r];
-            else {                                        // queue full (long reads, repetitive tiles): walk it here
-              const uint32_t ib4 = ibase4 + pos4;
-              for (uint32_t st = (uint32_t) bstart[code] + 4, en = bstart[code + 1]; st < en; ++st) {
-                const uint32_t v4 = (uint32_t) bpos[st] << 2;
-                if (interior || ib4 + v4 < dlen4) atomicAdd ((uint32_t*) ((char*) cnt + ((io4 + v4) & mask4)), 1u);
-              }
-            }
-          }
-        }
-      }
-    }
-    __syncthreads ();
-    {
-      const uint32_t qn_ = s_qn[tile & 1], qn = qn_ < QG_TSEED_QCAP ? qn_ : QG_TSEED_QCAP;
-      if (tid == 0) s_qn[(tile & 1) ^ 1] = 0;              // nobody touches it between the barrier above and the one below
-      for (uint32_t q0 = (uint32_t) wid * 32u; q0 < qn; q0 += (uint32_t) T) {      // a warp per 32 queued positions: every lane has a tail
-        const uint32_t q = q0 + (uint32_t) lane;
-        const bool have = q < qn;
-        const uint32_t en_ = have ? queue[q] : 0u;
-        const uint32_t code = en_ >> 16, pos4 = en_ & 0xFFFFu;
-        const uint32_t io4 = tbo4 + pos4, ib4 = ibase4 + pos4;
-        uint32_t st = have ? (uint32_t) bstart[code] + 4 : 0u;
-        const uint32_t en = have ? (uint32_t) bstart[code + 1] : 0u;
-        while (__any_sync (QG_FULL_MASK, st < en)) {
-          const bool act = st < en;
-          const uint32_t v4 = (uint32_t) bpos[act ? st : 0u] << 2;
-          QG_RED_IF (cnt, (io4 + v4) & mask4, act && (interior || ib4 + v4 < dlen4), dummy_off);
-          st += act ? 1u : 0u;
+        if (__any_sync (QG_FULL_MASK, more)) {            // buckets longer than four: continue from the full bucket array
+          uint32_t st = 0, en = 0;
+          if (more) { st = (uint32_t) bstart[code] + 4; en = bstart[code + 1]; }
+          const uint32_t ib4 = ibase4 + pos4;
+          do {
+            const bool act = st < en;
+            const uint32_t v4 = (uint32_t) bpos[act ? st : 0u] << 2;
+            QG_RED_IF (cnt, (io4 + v4) & mask4, act && (interior || ib4 + v4 < dlen4), dummy_off);
+            st += act ? 1u : 0u;
+          } while (__any_sync (QG_FULL_MASK, st < en));
         }
       }
     }

@@ -394,7 +394,7 @@ static size_t qg_seed_smem_bytes (int k, uint32_t ymax, uint32_t* ring_out) {
 // the tile-sorted kernel (qg_seed_tile_kernel): k = 5 or 6, every read's diagonals fit the 32k-counter ring next to one tile
 static size_t qg_tseed_smem_bytes (int k, uint32_t ymax) {
   const uint32_t nk = 1u << (2 * k);
-  return (size_t) QG_TSEED_RING * 4 + (size_t) (nk + 1) * 8 + (size_t) ((nk + 2 + 3) & ~3u) * 2 + (size_t) ((ymax + 2 + 1) & ~1u) * 2 + (QG_TSEED_ESTEP / 32 + 2) * 4 + 32 * 4 + (size_t) QG_TSEED_QCAP * 4;
+  return (size_t) QG_TSEED_RING * 4 + (size_t) (nk + 1) * 8 + (size_t) ((nk + 2 + 3) & ~3u) * 2 + (size_t) ((ymax + 2 + 1) & ~1u) * 2 + (QG_TSEED_ESTEP / 32 + 2) * 4 + 32 * 4;
 }
 static bool qg_seed_use_tiles (qg_ctx* ctx, int k, uint32_t ymax) {
   if (getenv ("QG_SEED_LEGACY")) return false;                 // tests / profiling: the round-1 kernel

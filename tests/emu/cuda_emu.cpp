@@ -1,3 +1,4 @@
+#include <mutex>
 // TEST INFRASTRUCTURE ONLY -- see cuda_emu.h.
 #include "cuda_emu.h"
 
@@ -6,7 +7,12 @@ thread_local uint3_e t_threadIdx, t_blockIdx;
 thread_local dim3 t_blockDim, t_gridDim;
 thread_local BlockState* t_block;
 
+// statically declared __shared__ variables are plain statics here, so one block runs at a time -- also when several host
+// threads (the contexts of a qg_pool) launch concurrently
+static std::mutex g_launch_mx;
+
 void launch (dim3 grid, dim3 block, size_t smem, const std::function<void ()>& body) {
+  std::lock_guard<std::mutex> one_launch (g_launch_mx);
   const unsigned nthreads = block.x * block.y * block.z;
   const unsigned nwarps = (nthreads + 31) / 32;
   BlockState bs;
