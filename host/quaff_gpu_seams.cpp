@@ -1,6 +1,8 @@
 // Seams A/B/C of the reference (QuaffAligner::align qmodel.cpp:2624, QuaffOverlapAligner::align qoverlap.cpp:312,
 // QuaffTrainer::getCounts qmodel.cpp:2005) routed to libquaffgpu.  The reference keeps everything else: flag parsing,
 // sequence loading, params / null model, the Alignment type and every output writer.
+#include <time.h>
+#include <cstdio>
 #include <fstream>
 #include <sstream>
 #include <algorithm>
@@ -40,6 +42,8 @@ bool quaffGpuParseArg (std::deque<std::string>& argvec) {
 namespace {
 struct Flat { std::vector<uint8_t> tok, qual; std::vector<uint64_t> off; bool quals; };
 
+// FastSeq::tokens / FastSeq::qualScores (fastseq.cpp:71-83, 101-109) for a whole set into flat arrays, through 256-entry
+// tables built from the reference's own per-character functions (one pass, no per-read vectors)
 Flat flatten (const vguard<FastSeq>& seqs, bool wantQual) {
   Flat f;
   f.quals = wantQual && !seqs.empty();
@@ -47,11 +51,23 @@ Flat flatten (const vguard<FastSeq>& seqs, bool wantQual) {
   if (wantQual && !f.quals)
     for (const auto& s : seqs)
       Require (!s.hasQual(), "-gpu: either all reads or no reads must carry quality scores (%s)", s.name.c_str());
-  f.off.push_back (0);
-  for (const auto& s : seqs) {
-    for (auto t : s.tokens (dnaAlphabet)) f.tok.push_back ((uint8_t) t);
-    if (f.quals) for (auto q : s.qualScores()) f.qual.push_back ((uint8_t) q);
-    f.off.push_back (f.tok.size());
+  int tokOf[256]; uint8_t qualOf[256];
+  for (int c = 0; c < 256; ++c) { tokOf[c] = c ? tokenize ((char) c, dnaAlphabet) : -1; qualOf[c] = (uint8_t) FastSeq::qualScoreForChar ((char) c); }
+  f.off.resize (seqs.size() + 1);
+  f.off[0] = 0;
+  for (size_t n = 0; n < seqs.size(); ++n) f.off[n+1] = f.off[n] + seqs[n].length();
+  f.tok.resize (f.off.back());
+  if (f.quals) f.qual.resize (f.off.back());
+  for (size_t n = 0; n < seqs.size(); ++n) {
+    const FastSeq& s = seqs[n];
+    uint8_t* t = f.tok.data() + f.off[n];
+    const size_t len = s.length();
+    for (size_t i = 0; i < len; ++i) {
+      const int v = tokOf[(unsigned char) s.seq[i]];
+      if (v < 0) { cerr << "Unknown symbol " << s.seq[i] << " in sequence " << s.name << endl; throw; }
+      t[i] = (uint8_t) v;
+    }
+    if (f.quals) { uint8_t* q = f.qual.data() + f.off[n]; for (size_t i = 0; i < len; ++i) q[i] = qualOf[(unsigned char) s.qual[i]]; }
   }
   return f;
 }
@@ -61,6 +77,14 @@ struct Gpu {
   Gpu () : ctx (NULL) { Require (qg_create (&ctx, quaffGpuDevice) == QG_OK, "-gpu: %s", qg_last_error (NULL)); }
   ~Gpu () { qg_destroy (ctx); }
   void ok (int rc) const { Require (rc == QG_OK, "-gpu: %s", qg_last_error (ctx)); }
+};
+
+// QUAFF_GPU_TRACE=1: wall-clock stamps of the seam's host phases on stderr
+struct Trace {
+  bool on; double t0;
+  static double now () { struct timespec ts; clock_gettime (CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
+  Trace () : on (getenv ("QUAFF_GPU_TRACE") != NULL), t0 (now()) { }
+  void mark (const char* what) { if (on) { const double t = now(); fprintf (stderr, "[quaff-gpu] %-28s %8.3f s\n", what, t - t0); t0 = t; } }
 };
 
 size_t envSize (const char* name, size_t dflt) { const char* v = getenv (name); return (v && *v) ? (size_t) strtoull (v, NULL, 10) : dflt; }
@@ -99,6 +123,17 @@ ScoreTables tables (const QuaffScores& qs) {
     t.insert[i * QG_NQ1 + QG_NQUAL] = qs.insert[i].logSymProb;
   }
   return t;
+}
+
+// QuaffNullParams::logLikelihood (qmodel.cpp:1875-1890) for every sequence of a flattened set: the library's table-driven
+// form of the same sum (same addends, same order); the reference evaluates a negative-binomial pdf per base (~1.4 ms per 8 kb read)
+std::vector<double> nullLogLikes (const QuaffNullParams& nullModel, const Flat& f, const vguard<FastSeq>& seqs) {
+  double pqr[12];
+  for (int t = 0; t < 4; ++t) { pqr[3*t] = nullModel.null[t].symProb; pqr[3*t+1] = nullModel.null[t].qualTrialSuccessProb; pqr[3*t+2] = nullModel.null[t].qualNumSuccessfulTrials; }
+  std::vector<double> ll (seqs.size());
+  for (size_t n = 0; n < seqs.size(); ++n)
+    ll[n] = qg_null_loglike (nullModel.nullEmit, pqr, f.tok.data() + f.off[n], seqs[n].hasQual() ? f.qual.data() + f.off[n] : NULL, f.off[n+1] - f.off[n]);
+  return ll;
 }
 
 template<class Setter>
@@ -146,6 +181,36 @@ Alignment alignmentFromPath (const FastSeq& x, const FastSeq& y, uint32_t xStart
   align.score = score;
   return align;
 }
+// -format sam without the gapped rows: the record Alignment::writeSam (qmodel.cpp:608-616) prints for the alignment
+// alignmentFromPath would build, straight from the op path.  Coordinates go through the reference's own
+// SeqIntervalCoords::compose, in the order alignmentFromPath / Alignment::revcomp / FastSeq::revcomp apply it; the CIGAR is
+// the run-length of the ops (cigarString, qmodel.cpp:625-653: letter then count), reversed when the reference row is a
+// reverse strand.  The reference's cigarString re-allocates the whole string per run and its revcomp() copies both rows:
+// ~0.5 ms per 8 kb read, more than the GPU needs for the alignment itself.
+void writeSamRecord (std::ostream& out, const FastSeq& x, const FastSeq& y, uint32_t xStart, uint32_t xEnd, const uint8_t* path, uint64_t n, double score) {
+  SeqIntervalCoords s0 = SeqIntervalCoords (x.name, xStart, xEnd, false).compose (x.source);
+  SeqIntervalCoords s1 = SeqIntervalCoords (y.name, 1, y.length(), false).compose (y.source);
+  const bool flip = s0.rev;
+  if (flip) {                                              // revcomp().writeSam (out): both gapped rows reverse-complemented
+    s0 = SeqIntervalCoords ("Ref", 1, (SeqIdx) n, true).compose (s0);
+    s1 = SeqIntervalCoords ("Read", 1, (SeqIdx) n, true).compose (s1);
+  }
+  static const char letter[3] = { 'M', 'I', 'D' };         // QG_OP_MATCH, QG_OP_INSERT (gap in the reference row), QG_OP_DELETE
+  std::string cigar;
+  cigar.reserve (n / 2 + 16);
+  char buf[24];
+  for (uint64_t t = 0; t < n; ) {
+    const uint8_t op = flip ? path[n - 1 - t] : path[t];
+    uint64_t e = t + 1;
+    while (e < n && (flip ? path[n - 1 - e] : path[e]) == op) ++e;
+    cigar += letter[op];
+    const int len = snprintf (buf, sizeof (buf), "%llu", (unsigned long long) (e - t));
+    cigar.append (buf, len);
+    t = e;
+  }
+  const int flag = s1.rev ? 16 : 0;
+  out << s1.name << '\t' << flag << '\t' << s0.name << '\t' << s0.start << "\t0\t" << cigar << "\t*\t0\t0\t*\t*\tAS:i:" << ((int) round (score)) << endl;
+}
 }  // namespace
 
 // ---- seam A -------------------------------------------------------------------------------------------------------
@@ -167,8 +232,14 @@ struct AlignSink {
     AlignSink& s = *(AlignSink*) user;
     std::vector<Alignment> al;
     std::ostringstream os;
+    const bool samFast = !s.toFile && s.aligner.format == QuaffAlignmentPrinter::SamAlignment && !getenv ("QUAFF_GPU_GENERIC_WRITER");
     for (size_t r = 0; r < n; ++r)
       if (best[r] != 0xFFFFFFFFu) {
+        if (samFast) {
+          if (score[r] >= s.aligner.logOddsThreshold)
+            writeSamRecord (os, s.x[best[r]], s.y[first + r], xs[r], xe[r], paths + off[r], off[r+1] - off[r], score[r]);
+          continue;
+        }
         Alignment a = alignmentFromPath (s.x[best[r]], s.y[first + r], xs[r], xe[r], paths + off[r], off[r+1] - off[r], score[r], s.local);
         if (s.toFile) al.push_back (a); else s.aligner.writeAlignment (os, a);
       }
@@ -194,22 +265,27 @@ struct AlignSink {
 
 void quaffGpuAlign (QuaffAligner& aligner, std::ostream& out, const vguard<FastSeq>& x, const vguard<FastSeq>& y,
                     const QuaffParams& params, const QuaffNullParams& nullModel, QuaffDPConfig& config) {
+  Trace tr;
   const Flat fx = flatten (x, false), fy = flatten (y, true);
+  tr.mark ("tokenise (flatten)");
   const qg_dpconfig gc = gpuConfig (config);
-  std::vector<double> nullLL (y.size());
-  for (size_t n = 0; n < y.size(); ++n) nullLL[n] = nullModel.logLikelihood (y[n]);
+  const std::vector<double> nullLL = nullLogLikes (nullModel, fy, y);
+  tr.mark ("null-model log-likelihoods");
   if (!aligner.printAllAlignments) {
     // chunks of reads over every context of every device (QUAFF_GPU_CHUNK reads each, QUAFF_GPU_CONTEXTS contexts per device)
     const size_t chunk = std::max<size_t> (1, envSize ("QUAFF_GPU_CHUNK", 1536));
     const size_t nChunks = (y.size() + chunk - 1) / chunk, nDev = std::max<size_t> (1, quaffGpuDevices.size());
     const size_t perDevice = std::max<size_t> (1, std::min<size_t> (envSize ("QUAFF_GPU_CONTEXTS", 2), (nChunks + nDev - 1) / nDev));
     GpuPool g ((int) perDevice);
+    tr.mark ("contexts");
     g.ok (qg_pool_set_refs (g.pool, x.size(), fx.tok.data(), fx.off.data()));
     setAlignModel (g, params);
+    tr.mark ("reference set + model");
     aligner.writeAlignmentHeader (out, x, true);
     AlignSink sink (aligner, out, x, y, config.local, chunk);
     g.ok (qg_pool_align_reads (g.pool, &gc, y.size(), fy.tok.data(), fy.quals ? fy.qual.data() : NULL, fy.off.data(), nullLL.data(), chunk,
                                AlignSink::onChunk, &sink));
+    tr.mark ("align + format + write");
     return;
   }
   Gpu g;
@@ -313,8 +389,8 @@ QuaffParamCounts quaffGpuGetCounts (QuaffTrainer& trainer, const vguard<FastSeq>
   if (getenv ("QUAFF_GPU_EXACT")) g.ok (qg_pool_set_option (g.pool, QG_OPT_FB_EXACT, 1));
   const qg_dpconfig gc = gpuConfig (config);
   const size_t nx = x.size(), ny = y.size();
-  std::vector<double> nullLL (ny), yLL (ny);
-  for (size_t n = 0; n < ny; ++n) nullLL[n] = nullModel.logLikelihood (y[n]);
+  std::vector<double> yLL (ny);
+  const std::vector<double> nullLL = nullLogLikes (nullModel, fy, y);
   std::vector<uint32_t> so (nx * ny, 0), soLen (ny);
   for (size_t n = 0; n < ny; ++n) {
     soLen[n] = (uint32_t) sortOrder[n].size();

@@ -32,17 +32,24 @@ extern "C" int qg_pool_create (qg_pool** out, const int* devices, int n_devices,
   if (!out || n_devices < 1 || contexts_per_device < 1 || !devices) return QG_ERR_INVALID;
   *out = nullptr;
   qg_pool* p = new qg_pool;
-  for (int c = 0; c < contexts_per_device; ++c)              // context order: device-major inside every round, so that
-    for (int d = 0; d < n_devices; ++d) {                      // the first n_devices workers sit on different devices
-      qg_ctx* x = nullptr;
-      const int rc = qg_create (&x, devices[d]);
-      if (rc != QG_OK) {
-        qg_pool_create_error = qg_last_error (nullptr);
-        for (qg_ctx* y : p->ctx) qg_destroy (y);
-        delete p;
-        return rc;
-      }
-      p->ctx.push_back (x); p->device.push_back (devices[d]);
+  // context order: device-major inside every round, so that the first n_devices workers sit on different devices.
+  // Created concurrently: the first touch of a device (CUDA context creation) dominates and is independent per device.
+  const int n = n_devices * contexts_per_device;
+  p->ctx.assign (n, nullptr); p->device.resize (n);
+  std::vector<int> rcs (n, QG_OK);
+  std::vector<std::string> errs (n);
+  std::vector<std::thread> th;
+  for (int w = 0; w < n; ++w) {
+    p->device[w] = devices[w % n_devices];
+    th.emplace_back ([&, w] { rcs[w] = qg_create (&p->ctx[w], p->device[w]); if (rcs[w] != QG_OK) errs[w] = qg_last_error (nullptr); });
+  }
+  for (auto& t : th) t.join ();
+  for (int w = 0; w < n; ++w)
+    if (rcs[w] != QG_OK) {
+      qg_pool_create_error = errs[w];
+      for (qg_ctx* y : p->ctx) if (y) qg_destroy (y);
+      delete p;
+      return rcs[w];
     }
   *out = p;
   return QG_OK;

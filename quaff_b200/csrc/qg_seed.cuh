@@ -331,7 +331,12 @@ qg_sort_tiles_kernel (const qg_tile_job* __restrict__ jobs, const uint16_t* __re
 //   ring slot of diagonal d = (d + span + off) & (ring - 1); off in 0..3 makes the item's first diagonal 16-byte aligned
 // The hit statistic is the sum of the counters the emit scan reads (every hit of the item is one increment of one of them).
 template<bool COUNTS>
-__global__ void __launch_bounds__ (QG_TSEED_THREADS, 1)
+__global__ void
+#if defined(QG_TSEED_MAXNREG) && !defined(QG_EMU)
+__maxnreg__ (QG_TSEED_MAXNREG)       /* leaves register file next to the one resident CTA for the DP kernels of the other contexts */
+#else
+__launch_bounds__ (QG_TSEED_THREADS, 1)
+#endif
 qg_seed_tile_kernel (const qg_seed_item* __restrict__ items, const qg_pair_desc* __restrict__ pairs,
                      const uint32_t* __restrict__ xsorted, const uint16_t* __restrict__ ycodes,
                      int k, int threshold, int half_band, uint32_t ymax, uint32_t run_cap,

@@ -15,7 +15,7 @@
 #include <map>
 #include <numeric>
 
-static qg_error g_create_error;
+static thread_local qg_error g_create_error;     // per thread: qg_last_error (NULL) reports the calling thread's last failed qg_create
 
 enum {
   SC_PAIRDESC = 0, SC_ITEMS, SC_ITEMRUNS, SC_ITEMNRUNS, SC_PAIRRUNS, SC_PAIRINFO, SC_PAIRCU, SC_FLAGS,
@@ -365,11 +365,18 @@ extern "C" int qg_scores_from_params (const qg_params* qp, double* match, double
 }
 
 extern "C" double qg_null_loglike (double null_emit, const double* null_pqr, const uint8_t* tok, const uint8_t* qual, uint64_t len) {
-  double ll = len * log (null_emit) + log (1. - null_emit);    // qmodel.cpp:1875-1890
+  // qmodel.cpp:1875-1890: the same addends in the same order (so the same bits); the two per-base terms are functions of
+  // (token, quality) only and are tabulated once per call instead of evaluated per base (three lgamma + two pow each)
+  double lsym[4], lq[4][QG_NQUAL];
+  for (int t = 0; t < 4; ++t) {
+    const double* d = null_pqr + 3 * t;
+    lsym[t] = log (d[0]);
+    if (qual) for (int k = 0; k < QG_NQUAL; ++k) lq[t][k] = qg_log_negbinom (k, d[1], d[2]);
+  }
+  double ll = len * log (null_emit) + log (1. - null_emit);
   for (uint64_t i = 0; i < len; ++i) {
-    const double* d = null_pqr + 3 * tok[i];
-    ll += log (d[0]);
-    if (qual) ll += qg_log_negbinom (qual[i], d[1], d[2]);
+    ll += lsym[tok[i]];
+    if (qual) ll += lq[tok[i]][qual[i]];
   }
   return ll;
 }
