@@ -275,7 +275,7 @@ void quaffGpuAlign (QuaffAligner& aligner, std::ostream& out, const vguard<FastS
     // chunks of reads over every context of every device (QUAFF_GPU_CHUNK reads each, QUAFF_GPU_CONTEXTS contexts per device)
     const size_t chunk = std::max<size_t> (1, envSize ("QUAFF_GPU_CHUNK", 1536));
     const size_t nChunks = (y.size() + chunk - 1) / chunk, nDev = std::max<size_t> (1, quaffGpuDevices.size());
-    const size_t perDevice = std::max<size_t> (1, std::min<size_t> (envSize ("QUAFF_GPU_CONTEXTS", 2), (nChunks + nDev - 1) / nDev));
+    const size_t perDevice = std::max<size_t> (1, std::min<size_t> (envSize ("QUAFF_GPU_CONTEXTS", 4), (nChunks + nDev - 1) / nDev));
     GpuPool g ((int) perDevice);
     tr.mark ("contexts");
     g.ok (qg_pool_set_refs (g.pool, x.size(), fx.tok.data(), fx.off.data()));

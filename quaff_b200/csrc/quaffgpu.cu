@@ -701,8 +701,25 @@ static int qg_envelope_stage_retry (qg_ctx* ctx, const qg_dpconfig* cfg, uint64_
 
 // The memory-guided mode and the general seeding path keep one 32-bit counter per diagonal per pair in HBM: the pair
 // list is cut into sub-batches whose counters fit the budget.
+// The E-step runs Forward over every pair, then Forward + Backward over the gated ones (qmodel.cpp:2247-2262 builds one
+// envelope per pair and uses it for both matrices): the first pass leaves its envelopes here, the second picks its pairs
+// out of them instead of seeding again.  Per thread = per calling context (one host thread drives a context at a time).
+struct qg_env_reuse { qg_env_result* keep = nullptr; const qg_env_result* src = nullptr; const std::vector<size_t>* pick = nullptr; };
+static thread_local qg_env_reuse g_env_reuse;
+
 static int qg_envelope_stage (qg_ctx* ctx, const qg_dpconfig* cfg, uint64_t cell_size, int x_set,
                               size_t n_pairs, const uint32_t* xi, const uint32_t* yi, qg_env_result& out) {
+  if (g_env_reuse.src && g_env_reuse.pick && g_env_reuse.pick->size () == n_pairs) {
+    const qg_env_result& S = *g_env_reuse.src;
+    out = qg_env_result ();
+    out.run_begin.push_back (0);
+    for (size_t p : *g_env_reuse.pick) {
+      out.runs.insert (out.runs.end (), S.runs.begin () + S.run_begin[p], S.runs.begin () + S.run_begin[p + 1]);
+      out.run_begin.push_back ((uint32_t) out.runs.size ());
+      out.cu.push_back (S.cu[p]); out.ndiag.push_back (S.ndiag[p]);
+    }
+    return QG_OK;
+  }
   const bool counters = cfg->sparse && (cfg->kmer_threshold < 0 || qg_seed_is_general (ctx, cfg, x_set, n_pairs, xi, yi));
   if (!counters) return qg_envelope_stage_retry (ctx, cfg, cell_size, x_set, n_pairs, xi, yi, out);
   const qg_seqset& X = ctx->seqs[x_set];
@@ -1431,6 +1448,7 @@ extern "C" int qg_forward (qg_ctx* ctx, const qg_dpconfig* cfg, size_t n_pairs, 
   QG_TRY (qg_check_ready (ctx, cfg));
   qg_env_result er;
   QG_TRY (qg_envelope_stage (ctx, cfg, 48, QG_REFS, n_pairs, xi, yi, er));
+  if (g_env_reuse.keep) *g_env_reuse.keep = er;
   {
     std::vector<size_t> wide, narrow;
     for (size_t p = 0; p < n_pairs; ++p) (qg_pair_is_wide (er, p) ? wide : narrow).push_back (p);
@@ -1708,10 +1726,16 @@ extern "C" int qg_estep (qg_ctx* ctx, const qg_dpconfig* cfg, int use_null, cons
   }
   first[ny] = xi.size ();
   std::vector<double> F (xi.size ());
-  if (!xi.empty ()) QG_TRY (qg_forward (ctx, cfg, xi.size (), xi.data (), yi.data (), F.data ()));
+  qg_env_result env_all;                                           // the Forward pass's envelopes, reused by the Backward pass
+  if (!xi.empty ()) {
+    g_env_reuse.keep = &env_all;
+    const int rc = qg_forward (ctx, cfg, xi.size (), xi.data (), yi.data (), F.data ());
+    g_env_reuse.keep = nullptr;
+    QG_TRY (rc);
+  }
 
   // 2. replay the gate in sortOrder order; collect the pairs that need Backward
-  std::vector<uint32_t> bxi, byi; std::vector<double> bw;
+  std::vector<uint32_t> bxi, byi; std::vector<double> bw; std::vector<size_t> bpick;
   std::vector<std::vector<double> > xyLL (ny, std::vector<double> (nx, -INFINITY));
   *loglike_sum = 0;
   for (size_t y = 0; y < ny; ++y) {
@@ -1722,7 +1746,7 @@ extern "C" int qg_estep (qg_ctx* ctx, const qg_dpconfig* cfg, int use_null, cons
       if (F[p] >= yLL - 20) gated.push_back (p);                  // MAX_TRAINING_LOG_DELTA, qmodel.cpp:23, 2252
       yLL = qg_host_lse (tab, yLL, F[p]);
     }
-    for (size_t p : gated) { bxi.push_back (xi[p]); byi.push_back ((uint32_t) y); bw.push_back (exp (F[p] - yLL)); }
+    for (size_t p : gated) { bxi.push_back (xi[p]); byi.push_back ((uint32_t) y); bw.push_back (exp (F[p] - yLL)); bpick.push_back (p); }
     y_loglike[y] = yLL;
     *loglike_sum += yLL;                                          // accumulate(yLogLike, 0.), qmodel.cpp:2420-2422
     // sortOrder := refs by descending F, cut at the first one below yLL - 20 (qmodel.cpp:2264-2270)
@@ -1737,7 +1761,13 @@ extern "C" int qg_estep (qg_ctx* ctx, const qg_dpconfig* cfg, int use_null, cons
 
   // 3. Backward on the gated pairs, posterior-weighted sum of QuaffCounts, then QuaffParamCounts (qmodel.cpp:407-417)
   std::vector<double> qc (nC, 0.0);
-  if (!bxi.empty ()) QG_TRY (qg_backward_counts (ctx, cfg, bxi.size (), bxi.data (), byi.data (), bw.data (), nullptr, nullptr, qc.data (), nullptr));
+  if (!bxi.empty ()) {
+    const bool reuse = env_all.run_begin.size () == xi.size () + 1 && !getenv ("QG_ESTEP_RESEED");
+    if (reuse) { g_env_reuse.src = &env_all; g_env_reuse.pick = &bpick; }
+    const int rc = qg_backward_counts (ctx, cfg, bxi.size (), bxi.data (), byi.data (), bw.data (), nullptr, nullptr, qc.data (), nullptr);
+    g_env_reuse.src = nullptr; g_env_reuse.pick = nullptr;
+    QG_TRY (rc);
+  }
   const size_t nEmit = 4 * nK * QG_NQUAL + 4 * QG_NQUAL;
   memcpy (param_counts, qc.data (), sizeof (double) * nEmit);
   const double *m2m = qc.data () + nEmit, *m2i = m2m + nG, *m2d = m2i + nG, *m2e = m2d + nG, *sc = m2e + nG;
