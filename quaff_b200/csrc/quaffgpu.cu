@@ -943,9 +943,13 @@ static bool qg_pair_is_wide (const qg_env_result& er, size_t p) {
 
 // mode 0: Viterbi (+ traceback of the pairs flagged in want); mode 1: Forward log-likelihood.  idx: the wide pairs'
 // positions in the caller's pair list; outputs are written at those positions.
+// mode 2: Forward with every cell kept, Backward + counts (qg_tile_backward_kernel); fb carries its inputs and outputs.
+struct qg_wide_fb { const double* weights = nullptr; double* back = nullptr; double* counts_sum = nullptr; double* counts_per_pair = nullptr; uint64_t nC = 0; };
+
 static int qg_wide_run (qg_ctx* ctx, const qg_dpconfig* cfg, const qg_env_result& er, const std::vector<size_t>& idx,
                         const uint32_t* xi, const uint32_t* yi, int mode, const uint8_t* want,
-                        double* score, uint32_t* x_start, uint32_t* x_end, std::vector<std::vector<uint8_t> >* paths) {
+                        double* score, uint32_t* x_start, uint32_t* x_end, std::vector<std::vector<uint8_t> >* paths,
+                        const qg_wide_fb* fb = nullptr) {
   const qg_seqset& X = ctx->seqs[QG_REFS];
   const qg_seqset& Y = ctx->seqs[QG_READS];
   size_t freeb = 0, totb = 0;
@@ -955,9 +959,11 @@ static int qg_wide_run (qg_ctx* ctx, const qg_dpconfig* cfg, const qg_env_result
   while (q0 < idx.size ()) {
     // ---- plan a batch of pairs under the memory budget
     std::vector<qg_wseg> segs; std::vector<qg_tile> tiles; std::vector<qg_wpair> wp; std::vector<long long> tables;
+    std::vector<qg_tile> btiles;                             // mode 2: tiles of the reversed matrices
     qg_dp_plan rpplan; std::map<uint32_t, uint64_t> rp_of_read;
-    uint64_t end_d = 0, bytes = 0, scratch_bytes = 0;
-    const uint64_t tile_bytes = (mode == 0 ? QG_TILE_WORDS * 4ull : 0) + (QG_TRH + QG_TCW) * 24ull + 2 * 16 + sizeof (qg_tile);
+    uint64_t end_d = 0, bytes = 0, scratch_bytes = 0, acc_rows = 0;
+    const uint64_t tile_bytes = (mode == 0 ? QG_TILE_WORDS * 4ull : 0) + (QG_TRH + QG_TCW) * 24ull + 2 * 16 + sizeof (qg_tile)
+                              + (mode == 2 ? QG_TILE_CELLS3 * 8 + (QG_TRH + QG_TCW) * 24ull + sizeof (qg_tile) : 0);
     size_t q1 = q0;
     while (q1 < idx.size ()) {
       const size_t p = idx[q1];
@@ -974,7 +980,8 @@ static int qg_wide_run (qg_ctx* ctx, const qg_dpconfig* cfg, const qg_env_result
       for (uint32_t r = er.run_begin[p]; r < er.run_begin[p + 1]; ++r)
         for (uint32_t b = 0; b < nRB; ++b) { int64_t aLo, aHi; col_blocks (er.runs[r].x, er.runs[r].y, b, &aLo, &aHi); ntile += (uint64_t) (aHi - aLo + 1); }
       const uint64_t nruns = er.run_begin[p + 1] - er.run_begin[p];
-      const uint64_t need = ntile * tile_bytes + nruns * ((uint64_t) nCB * nRB * 8 + (uint64_t) (xlen + 1) * 8) + 2ull * (xlen + ylen);
+      const uint64_t need = ntile * tile_bytes + nruns * ((uint64_t) nCB * nRB * 8 + (uint64_t) (xlen + 1) * 8 + (mode == 2 ? ((uint64_t) ylen + 2) * 64 : 0)) + 2ull * (xlen + ylen)
+                            + (mode == 2 && fb ? fb->nC * 8 : 0);
       if (q1 > q0 && (bytes + need > budget || tiles.size () + ntile > 0x7FFFFFF0ull)) break;
       if (need > budget || ntile > 0x7FFFFFF0ull) QG_FAIL (ctx, QG_ERR_UNSUPPORTED, "pair %zu needs %llu MB of device memory for its %llu tiles (budget %llu MB)", p,
                                   (unsigned long long) (need >> 20), (unsigned long long) ntile, (unsigned long long) (budget >> 20));
@@ -995,6 +1002,23 @@ static int qg_wide_run (qg_ctx* ctx, const qg_dpconfig* cfg, const qg_env_result
         ws.nCB = nCB; ws.nRB = nRB; ws.rp_off = it->second;
         ws.table_off = tables.size (); tables.resize (tables.size () + (size_t) nCB * nRB, -1);
         ws.end_off = end_d; end_d += (uint64_t) xlen + 1;
+        ws.acc_off = acc_rows; if (mode == 2) acc_rows += (uint64_t) ylen + 2;
+        if (mode == 2) {
+          // the reversed matrix of this run: band [xLen - yLen - dhi, xLen - yLen - dlo], its own block table (host only)
+          const int rlo = ((int) xlen - (int) ylen) - ws.dhi, rhi = ((int) xlen - (int) ylen) - ws.dlo;
+          std::vector<long long> rtab ((size_t) nCB * nRB, -1);
+          for (uint32_t b = 0; b < nRB; ++b) {
+            int64_t aLo, aHi; col_blocks (rlo, rhi, b, &aLo, &aHi);
+            for (int64_t a = aLo; a <= aHi; ++a) {
+              qg_tile t; t.seg = (uint32_t) segs.size (); t.a = (uint32_t) a; t.b = b; t.id = (uint32_t) btiles.size (); t.pad_ = 0;
+              t.left = a > 0 ? (int32_t) rtab[(size_t) (a - 1) * nRB + b] : -1;
+              t.up = b > 0 ? (int32_t) rtab[(size_t) a * nRB + (b - 1)] : -1;
+              t.diag = (a > 0 && b > 0) ? (int32_t) rtab[(size_t) (a - 1) * nRB + (b - 1)] : -1;
+              rtab[(size_t) a * nRB + b] = (long long) t.id;
+              btiles.push_back (t);
+            }
+          }
+        }
         long long* tab = tables.data () + ws.table_off;
         for (uint32_t b = 0; b < nRB; ++b) {
           int64_t aLo, aHi; col_blocks (ws.dlo, ws.dhi, b, &aLo, &aHi);
@@ -1020,8 +1044,11 @@ static int qg_wide_run (qg_ctx* ctx, const qg_dpconfig* cfg, const qg_env_result
       ++q1;
     }
     const uint64_t trace_words = mode == 0 ? (uint64_t) tiles.size () * QG_TILE_WORDS : 0;
-    const uint64_t col_d = (uint64_t) tiles.size () * QG_TRH * 3, row_d = (uint64_t) tiles.size () * QG_TCW * 3;
+    const uint64_t ntl = std::max (tiles.size (), btiles.size ());
+    const uint64_t col_d = ntl * QG_TRH * 3, row_d = ntl * QG_TCW * 3;
     const size_t np = wp.size ();
+    std::vector<qg_tile> bsorted (btiles);
+    std::stable_sort (bsorted.begin (), bsorted.end (), [] (const qg_tile& u, const qg_tile& v) { return u.a + u.b < v.a + v.b; });
     // tiles in wavefront order
     std::vector<qg_tile> sorted (tiles);
     std::stable_sort (sorted.begin (), sorted.end (), [] (const qg_tile& u, const qg_tile& v) { return u.a + u.b < v.a + v.b; });
@@ -1041,9 +1068,21 @@ static int qg_wide_run (qg_ctx* ctx, const qg_dpconfig* cfg, const qg_env_result
       QG_TRY (qg_reserve (ctx, ctx->scratch[SC_OUT2], sizeof (uint32_t) * (np + 1)));
       QG_TRY (qg_reserve (ctx, ctx->scratch[SC_OUT3], sizeof (uint32_t) * (np + 1)));
       QG_TRY (qg_reserve (ctx, ctx->scratch[SC_PATHSCR], scratch_bytes + 16));
+      if (mode == 2) {
+        QG_TRY (qg_reserve (ctx, ctx->scratch[SC_TRACE], sizeof (double) * ((uint64_t) tiles.size () * QG_TILE_CELLS3 + 1)));      // the Forward cells
+        QG_TRY (qg_upload (ctx, ctx->scratch[SC_ZE], bsorted.data (), sizeof (qg_tile) * bsorted.size ()));
+        QG_TRY (qg_reserve (ctx, ctx->scratch[SC_ZM], sizeof (qg_rowrec) * (acc_rows + 1)));
+        QG_TRY (qg_reserve (ctx, ctx->scratch[SC_MISC1], sizeof (double) * 12 * (segs.size () + 1)));
+        QG_TRY (qg_reserve (ctx, ctx->scratch[SC_PATHSCR], sizeof (double) * fb->nC * np + 16));
+        QG_CUDA (ctx, cudaMemsetAsync (ctx->scratch[SC_ZM].p, 0, sizeof (qg_rowrec) * (acc_rows + 1), ctx->stream));
+        QG_CUDA (ctx, cudaMemsetAsync (ctx->scratch[SC_MISC1].p, 0, sizeof (double) * 12 * (segs.size () + 1), ctx->stream));
+        QG_CUDA (ctx, cudaMemsetAsync (ctx->scratch[SC_PATHSCR].p, 0, sizeof (double) * fb->nC * np, ctx->stream));
+        ctx->stats.fwd_store_bytes += (uint64_t) tiles.size () * QG_TILE_CELLS3 * 8;
+      }
     }
     uint64_t cu = 0;
     for (size_t q = q0; q < q1; ++q) cu += er.cu[idx[q]];
+    if (mode == 2) cu *= 2;
     ctx->stats.cell_updates += cu;
     ctx->stats.n_segments += segs.size ();
     ctx->stats.trace_bytes += trace_words * 4;
@@ -1055,6 +1094,11 @@ static int qg_wide_run (qg_ctx* ctx, const qg_dpconfig* cfg, const qg_env_result
     a.i2i = ctx->model.i2i; a.i2m = ctx->model.i2m; a.d2d = ctx->model.d2d; a.d2m = ctx->model.d2m; a.local = cfg->local;
     a.trace = ctx->scratch[SC_TRACE].as<uint32_t> (); a.colbuf = ctx->scratch[SC_STORE].as<double> (); a.rowbuf = ctx->scratch[SC_ROWACC].as<double> ();
     a.tile_best = ctx->scratch[SC_ENDVALS].as<double> (); a.endvals = ctx->scratch[SC_ENDVALS].as<double> ();
+    if (mode == 2) {
+      a.fstore = ctx->scratch[SC_TRACE].as<double> (); a.btiles = ctx->scratch[SC_ZE].as<qg_tile> ();
+      a.tables = ctx->scratch[SC_MISC0].as<long long> (); a.pair_z = ctx->scratch[SC_OUT0].as<double> ();
+      a.rowacc = ctx->scratch[SC_ZM].as<double> (); a.seg_scal = ctx->scratch[SC_MISC1].as<double> ();
+    }
     {
       qg_timer tm (ctx, mode == 0 ? &ctx->stats.ms_viterbi : &ctx->stats.ms_forward);
       size_t t0 = 0;
@@ -1078,9 +1122,64 @@ static int qg_wide_run (qg_ctx* ctx, const qg_dpconfig* cfg, const qg_env_result
         QG_TRY (qg_check_launch (ctx, "qg_wide_forward_finalize_kernel"));
       }
     }
+    if (mode == 2) {
+      // Backward over the reversed matrices, one launch per tile anti-diagonal; then the counts as for banded pairs
+      const qg_seqset& Yr = ctx->seqs[QG_READS];
+      const qg_model_dev& m = ctx->model;
+      {
+        qg_timer tm (ctx, &ctx->stats.ms_backward);
+        size_t t0 = 0;
+        while (t0 < bsorted.size ()) {
+          size_t t1 = t0; const uint32_t w = bsorted[t0].a + bsorted[t0].b;
+          while (t1 < bsorted.size () && bsorted[t1].a + bsorted[t1].b == w) ++t1;
+          QG_LAUNCH (qg_tile_backward_kernel, (unsigned) (t1 - t0), 32, 0, ctx->stream, a, (uint32_t) t0);
+          QG_TRY (qg_check_launch (ctx, "qg_tile_backward_kernel"));
+          t0 = t1;
+        }
+        QG_LAUNCH (qg_wide_backward_finalize_kernel, (unsigned) ((np + 63) / 64), 64, 0, ctx->stream,
+                   ctx->scratch[SC_PAIRDP].as<qg_wpair> (), (uint32_t) np, ctx->scratch[SC_SEGS].as<qg_wseg> (),
+                   ctx->scratch[SC_ENDVALS].as<double> (), ctx->d_lse.as<double> (), ctx->scratch[SC_OUT1].as<double> ());
+        QG_TRY (qg_check_launch (ctx, "qg_wide_backward_finalize_kernel"));
+        // the scatter / reduce kernels of the banded path, over run and pair records in their layout
+        std::vector<qg_segment> fs (segs.size ()); std::vector<qg_pair_dp> fp (np);
+        for (size_t t = 0; t < segs.size (); ++t) {
+          qg_segment g; memset (&g, 0, sizeof (g));
+          g.pair = segs[t].pair; g.dlo = segs[t].dlo; g.width = (uint32_t) (segs[t].dhi - segs[t].dlo + 1); g.xlen = segs[t].xlen; g.ylen = segs[t].ylen;
+          g.xseq = segs[t].xseq; g.yseq = yi[idx[q0 + segs[t].pair]]; g.acc_off = segs[t].acc_off; g.seg_id = t;
+          fs[t] = g;
+        }
+        for (size_t q = 0; q < np; ++q) { qg_pair_dp d; memset (&d, 0, sizeof (d)); d.seg_begin = wp[q].seg_begin; d.seg_end = wp[q].seg_end; d.xlen = wp[q].xlen; d.ylen = wp[q].ylen; fp[q] = d; }
+        QG_TRY (qg_upload (ctx, ctx->scratch[SC_KEYS0], fs.data (), sizeof (qg_segment) * fs.size ()));
+        QG_TRY (qg_upload (ctx, ctx->scratch[SC_KEYS1], fp.data (), sizeof (qg_pair_dp) * np));
+        QG_LAUNCH (qg_counts_scatter_kernel, (unsigned) np, 256, 0, ctx->stream,
+                   ctx->scratch[SC_KEYS1].as<qg_pair_dp> (), ctx->scratch[SC_KEYS0].as<qg_segment> (),
+                   Yr.d_tok.as<uint8_t> (), Yr.d_qual.as<uint8_t> (), Yr.d_off.as<uint64_t> (),
+                   (const qg_rowrec*) ctx->scratch[SC_ZM].p, ctx->scratch[SC_MISC1].as<double> (),
+                   m.match_k, m.gap_k, fb->nC, ctx->scratch[SC_PATHSCR].as<double> ());
+        QG_TRY (qg_check_launch (ctx, "qg_counts_scatter_kernel"));
+        std::vector<double> wq (np, 1.0);
+        if (fb->weights) for (size_t q = 0; q < np; ++q) wq[q] = fb->weights[idx[q0 + q]];
+        QG_TRY (qg_upload (ctx, ctx->scratch[SC_VALS0], wq.data (), sizeof (double) * np));
+        QG_TRY (qg_reserve (ctx, ctx->scratch[SC_VALS1], sizeof (double) * (fb->nC + 1)));
+        QG_CUDA (ctx, cudaMemsetAsync (ctx->scratch[SC_VALS1].p, 0, sizeof (double) * fb->nC, ctx->stream));
+        QG_LAUNCH (qg_counts_reduce_kernel, (unsigned) ((fb->nC + 127) / 128), 128, 0, ctx->stream,
+                   ctx->scratch[SC_PATHSCR].as<double> (), ctx->scratch[SC_VALS0].as<double> (), (uint32_t) np, fb->nC, ctx->scratch[SC_VALS1].as<double> ());
+        QG_TRY (qg_check_launch (ctx, "qg_counts_reduce_kernel"));
+      }
+      std::vector<double> part (fb->nC), bk (np);
+      QG_TRY (qg_download (ctx, part.data (), ctx->scratch[SC_VALS1].p, sizeof (double) * fb->nC));
+      if (fb->counts_sum) for (uint64_t k = 0; k < fb->nC; ++k) fb->counts_sum[k] += part[k];
+      QG_TRY (qg_download (ctx, bk.data (), ctx->scratch[SC_OUT1].p, sizeof (double) * np));
+      if (fb->back) for (size_t q = 0; q < np; ++q) fb->back[idx[q0 + q]] = bk[q];
+      if (fb->counts_per_pair) {
+        std::vector<double> pp (fb->nC * np);
+        QG_TRY (qg_download (ctx, pp.data (), ctx->scratch[SC_PATHSCR].p, sizeof (double) * fb->nC * np));
+        for (size_t q = 0; q < np; ++q) memcpy (fb->counts_per_pair + (uint64_t) idx[q0 + q] * fb->nC, pp.data () + q * fb->nC, sizeof (double) * fb->nC);
+      }
+    }
     std::vector<double> sc (np);
     QG_TRY (qg_download (ctx, sc.data (), ctx->scratch[SC_OUT0].p, sizeof (double) * np));
-    for (size_t q = 0; q < np; ++q) score[idx[q0 + q]] = sc[q];
+    if (score) for (size_t q = 0; q < np; ++q) score[idx[q0 + q]] = sc[q];
     if (mode == 0 && x_start) {
       std::vector<uint32_t> plen (np), xs (np), xe (np);
       uint32_t flag = 0;
@@ -1551,6 +1650,37 @@ extern "C" int qg_backward_counts (qg_ctx* ctx, const qg_dpconfig* cfg, size_t n
   const uint64_t nC = qg_counts_size (m.match_k, m.gap_k);
   qg_env_result er;
   QG_TRY (qg_envelope_stage (ctx, cfg, 48, QG_REFS, n_pairs, xi, yi, er));
+  {
+    // pairs with runs too wide for one CTA take the tiled path (qg_tile.cuh: log space, every Forward cell kept); the
+    // others go through this function again on their own, with the envelopes already computed
+    std::vector<size_t> wide, narrow;
+    for (size_t p = 0; p < n_pairs; ++p) (qg_pair_is_wide (er, p) ? wide : narrow).push_back (p);
+    if (!wide.empty ()) {
+      std::vector<double> sum (nC, 0.0);
+      if (!narrow.empty ()) {
+        std::vector<uint32_t> nx (narrow.size ()), ny (narrow.size ());
+        std::vector<double> nw (narrow.size (), 1.0), nf (narrow.size ()), nb (narrow.size ()), npp;
+        for (size_t q = 0; q < narrow.size (); ++q) { nx[q] = xi[narrow[q]]; ny[q] = yi[narrow[q]]; if (weights) nw[q] = weights[narrow[q]]; }
+        if (counts_per_pair) npp.resize (nC * narrow.size ());
+        const qg_env_reuse saved = g_env_reuse;
+        g_env_reuse.keep = nullptr; g_env_reuse.src = &er; g_env_reuse.pick = &narrow;
+        const int rc = qg_backward_counts (ctx, cfg, narrow.size (), nx.data (), ny.data (), weights ? nw.data () : nullptr, nf.data (), nb.data (),
+                                           sum.data (), counts_per_pair ? npp.data () : nullptr);
+        g_env_reuse = saved;
+        QG_TRY (rc);
+        for (size_t q = 0; q < narrow.size (); ++q) {
+          if (fwd_loglike) fwd_loglike[narrow[q]] = nf[q];
+          if (back_loglike) back_loglike[narrow[q]] = nb[q];
+          if (counts_per_pair) memcpy (counts_per_pair + (uint64_t) narrow[q] * nC, npp.data () + q * nC, sizeof (double) * nC);
+        }
+      }
+      qg_wide_fb fb; fb.weights = weights; fb.back = back_loglike; fb.counts_sum = sum.data (); fb.counts_per_pair = counts_per_pair; fb.nC = nC;
+      QG_TRY (qg_wide_run (ctx, cfg, er, wide, xi, yi, 2, nullptr, fwd_loglike, nullptr, nullptr, nullptr, &fb));
+      if (counts_sum) memcpy (counts_sum, sum.data (), sizeof (double) * nC);
+      QG_CUDA (ctx, qg_sync (ctx));
+      return QG_OK;
+    }
+  }
   size_t freeb = 0, totb = 0;
   QG_CUDA (ctx, cudaMemGetInfo (&freeb, &totb));
   // what this context already holds for the store is available to it again: count it with the free memory

@@ -169,6 +169,7 @@ def test_emu_wide_runs_tiled(emu_lib, oracle, monkeypatch):
         for cfg in (api.dp_config(kmer_threshold=3, band_size=20), api.dp_config(kmer_threshold=6, local=False)):
             pc.check_viterbi(g, oracle, x, reads, s_or, cfg, xi, yi)
             pc.check_forward(g, oracle, x, reads, s_or, cfg, xi, yi)
+            pc.check_backward(g, oracle, x, reads, s_or, cfg, xi, yi)      # Backward + counts on tiles (qg_tile_backward_kernel)
     finally:
         g.close()
 

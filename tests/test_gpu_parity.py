@@ -1,4 +1,6 @@
 """-m gpu: the CUDA library on a real B200, through the C ABI, against the oracle."""
+import os
+
 import numpy as np
 import pytest
 
@@ -159,7 +161,8 @@ def test_probability_space_order2_and_global(gpu, oracle):
 
 def test_wide_runs_tiled(gpu, oracle):
     """-kmatchoff on a 9 kb reference: one run of > 8192 diagonals per pair goes through the i-space tile
-    wavefront (qg_tile.cuh); Viterbi score / interval / path and Forward stay bit-exact"""
+    wavefront (qg_tile.cuh); Viterbi score / interval / path and Forward stay bit-exact, Backward + counts (tiles over the
+    reversed matrix) within 1e-9, and the E-step (count / train -kmatchoff) runs on top of them"""
     x, reads = pc.make_workload(ref_len=9000, n_reads=2, read_len=1500, seed=23)
     qp = pc.default_params()
     gpu.set_refs(x); gpu.set_reads(reads); gpu.set_params(qp)
@@ -169,6 +172,10 @@ def test_wide_runs_tiled(gpu, oracle):
         cfg = api.dp_config(sparse=False, local=local)
         pc.check_viterbi(gpu, oracle, x, reads, s_or, cfg, xi, yi)
         pc.check_forward(gpu, oracle, x, reads, s_or, cfg, xi, yi)
+        pc.check_backward(gpu, oracle, x, reads, s_or, cfg, xi, yi)
+    from quaff_b200.params import QuaffNullParams
+    nullp = QuaffNullParams.load(os.path.join(os.path.dirname(__file__), "golden", "testquaffnullparams.json"))
+    pc.check_estep(gpu, oracle, x, reads, s_or, nullp, api.dp_config(sparse=False), n_iter=1)
 
 
 def test_wide_and_narrow_pairs_mixed(gpu, oracle, workload, monkeypatch):
@@ -189,6 +196,7 @@ def test_wide_and_narrow_pairs_mixed(gpu, oracle, workload, monkeypatch):
     monkeypatch.setenv("QG_WIDE_MIN_DIAGS", str((widths[0] + widths[-1]) // 2))   # pairs on both sides of the threshold
     a1 = gpu.align_reads(cfg, null_ll)
     f1 = pc.check_forward(gpu, oracle, x, reads, s_or, cfg, xi, yi)
+    pc.check_backward(gpu, oracle, x, reads, s_or, cfg, xi, yi)           # wide and banded pairs in one call: tiles + the banded kernels
     monkeypatch.delenv("QG_WIDE_MIN_DIAGS")
     assert np.array_equal(a0["best_ref"], a1["best_ref"]) and np.array_equal(a0["score"], a1["score"])
     assert np.array_equal(a0["x_start"], a1["x_start"]) and np.array_equal(a0["x_end"], a1["x_end"])
