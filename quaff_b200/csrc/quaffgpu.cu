@@ -13,6 +13,7 @@
 #include <cub/device/device_segmented_radix_sort.cuh>
 #endif
 #include <map>
+#include <functional>
 #include <numeric>
 
 static thread_local qg_error g_create_error;     // per thread: qg_last_error (NULL) reports the calling thread's last failed qg_create
@@ -1638,11 +1639,23 @@ static int qg_launch_backward (qg_ctx* ctx, const qg_dp_plan& plan, qg_fill_args
   return QG_OK;
 }
 
+// The E-step's single pass (qg_estep): pair groups (one per read) that a memory batch must not split, and a callback that
+// turns a batch's Forward results into its posterior weights once they are on the host.  QG_RETRY_TWO_PASS: the batch
+// contains wide pairs, which this form does not serve -- the caller falls back to Forward first, Backward second.
+#define QG_RETRY_TWO_PASS (-1000)
+struct qg_weight_hook {
+  const std::vector<size_t>* group_first = nullptr;         // [n_groups + 1] pair indices
+  std::function<void (size_t p0, size_t p1, const double* fwd, double* w)> fn;
+};
+static thread_local const qg_weight_hook* g_weight_hook = nullptr;
+
 extern "C" int qg_backward_counts (qg_ctx* ctx, const qg_dpconfig* cfg, size_t n_pairs, const uint32_t* xi, const uint32_t* yi,
                                    const double* weights, double* fwd_loglike, double* back_loglike,
                                    double* counts_sum, double* counts_per_pair) {
   if (ctx) cudaSetDevice (ctx->device);                    // the caller may be a host thread that never selected this context's GPU
   if (!ctx || !cfg || !xi || !yi) return QG_ERR_INVALID;
+  const qg_weight_hook* hook = g_weight_hook;
+  g_weight_hook = nullptr;                                  // this call only (the wide/narrow split below re-enters)
   QG_TRY (qg_check_ready (ctx, cfg));
   const qg_seqset& Y = ctx->seqs[QG_READS];
   if (!Y.has_qual) QG_FAIL (ctx, QG_ERR_INVALID, "Forward-Backward requires quality scores (qmodel.cpp:1398)");
@@ -1655,6 +1668,7 @@ extern "C" int qg_backward_counts (qg_ctx* ctx, const qg_dpconfig* cfg, size_t n
     // others go through this function again on their own, with the envelopes already computed
     std::vector<size_t> wide, narrow;
     for (size_t p = 0; p < n_pairs; ++p) (qg_pair_is_wide (er, p) ? wide : narrow).push_back (p);
+    if (!wide.empty () && hook) return QG_RETRY_TWO_PASS;
     if (!wide.empty ()) {
       std::vector<double> sum (nC, 0.0);
       if (!narrow.empty ()) {
@@ -1689,16 +1703,34 @@ extern "C" int qg_backward_counts (qg_ctx* ctx, const qg_dpconfig* cfg, size_t n
   qg_dbuf& dSum = ctx->scratch[SC_OUT3];
   QG_TRY (qg_reserve (ctx, dSum, sizeof (double) * (nC + 1)));
   QG_CUDA (ctx, cudaMemsetAsync (dSum.p, 0, sizeof (double) * nC, ctx->stream));
-  size_t p0 = 0;
+  std::vector<double> hook_w, hook_f;
+  size_t p0 = 0, g0 = 0;                                     // g0: first group of the batch (hook only)
   while (p0 < n_pairs) {
     size_t p1 = p0; uint64_t bytes = 0;
-    while (p1 < n_pairs) {
+    auto pair_bytes = [&] (size_t p, uint64_t* out) -> int {
       uint64_t b = nC * 8;
-      for (uint32_t r = er.run_begin[p1]; r < er.run_begin[p1 + 1]; ++r) {
+      for (uint32_t r = er.run_begin[p]; r < er.run_begin[p + 1]; ++r) {
         int R, nw; const uint32_t width = (uint32_t) (er.runs[r].y - er.runs[r].x + 1);
-        if (qg_pick_R (width, &R, &nw) != QG_OK) QG_FAIL (ctx, QG_ERR_UNSUPPORTED, "pair %zu: a run of %u consecutive diagonals exceeds the %d this build fills with one CTA", p1, width, 256 * QG_MAX_NW);
-        b += ((uint64_t) Y.len (yi[p1]) + 32ull * nw + 1) * 3 * 32ull * nw * R * 8 + ((uint64_t) Y.len (yi[p1]) + 2) * 64;
+        if (qg_pick_R (width, &R, &nw) != QG_OK) QG_FAIL (ctx, QG_ERR_UNSUPPORTED, "pair %zu: a run of %u consecutive diagonals exceeds the %d this build fills with one CTA", p, width, 256 * QG_MAX_NW);
+        b += ((uint64_t) Y.len (yi[p]) + 32ull * nw + 1) * 3 * 32ull * nw * R * 8 + ((uint64_t) Y.len (yi[p]) + 2) * 64;
       }
+      *out = b; return QG_OK;
+    };
+    if (hook) {
+      // whole groups (all pairs of a read) per batch: the weights of a read need the Forward results of all its pairs
+      const std::vector<size_t>& gf = *hook->group_first;
+      size_t g1 = g0;
+      while (g1 + 1 < gf.size ()) {
+        uint64_t gb = 0;
+        for (size_t p = gf[g1]; p < gf[g1 + 1]; ++p) { uint64_t b; QG_TRY (pair_bytes (p, &b)); gb += b; }
+        if (g1 > g0 && bytes + gb > budget) break;
+        bytes += gb; ++g1;
+      }
+      p1 = gf[g1]; g0 = g1;
+      if (p1 == p0) { if (g1 + 1 >= gf.size ()) break; continue; }      // empty groups only
+    } else
+    while (p1 < n_pairs) {
+      uint64_t b; QG_TRY (pair_bytes (p1, &b));
       if (p1 > p0 && bytes + b > budget) break;
       bytes += b; ++p1;
     }
@@ -1795,6 +1827,13 @@ extern "C" int qg_backward_counts (qg_ctx* ctx, const qg_dpconfig* cfg, size_t n
                  m.match_k, m.gap_k, nC, ctx->scratch[SC_PATHSCR].as<double> ());
       QG_TRY (qg_check_launch (ctx, "qg_counts_scatter_kernel"));
       const double* dW = nullptr;
+      if (hook) {
+        // the batch's Forward results -> its posterior weights (the host waits here; Backward and the scatter are already queued)
+        hook_f.resize (np); hook_w.assign (np, 0.0);
+        QG_TRY (qg_download (ctx, hook_f.data (), ctx->scratch[SC_OUT0].p, sizeof (double) * np));
+        hook->fn (p0, p1, hook_f.data (), hook_w.data ());
+        QG_TRY (qg_upload (ctx, ctx->scratch[SC_OUT2], hook_w.data (), sizeof (double) * np)); dW = ctx->scratch[SC_OUT2].as<double> ();
+      } else
       if (weights) { QG_TRY (qg_upload (ctx, ctx->scratch[SC_OUT2], weights + p0, sizeof (double) * np)); dW = ctx->scratch[SC_OUT2].as<double> (); }
       QG_LAUNCH (qg_counts_reduce_kernel, (unsigned) ((nC + 127) / 128), 128, 0, ctx->stream,
                  ctx->scratch[SC_PATHSCR].as<double> (), dW, (uint32_t) np, nC, dSum.as<double> ());
@@ -1856,29 +1895,23 @@ extern "C" int qg_estep (qg_ctx* ctx, const qg_dpconfig* cfg, int use_null, cons
   }
   first[ny] = xi.size ();
   std::vector<double> F (xi.size ());
-  qg_env_result env_all;                                           // the Forward pass's envelopes, reused by the Backward pass
-  if (!xi.empty ()) {
-    g_env_reuse.keep = &env_all;
-    const int rc = qg_forward (ctx, cfg, xi.size (), xi.data (), yi.data (), F.data ());
-    g_env_reuse.keep = nullptr;
-    QG_TRY (rc);
-  }
-
-  // 2. replay the gate in sortOrder order; collect the pairs that need Backward
-  std::vector<uint32_t> bxi, byi; std::vector<double> bw; std::vector<size_t> bpick;
   std::vector<std::vector<double> > xyLL (ny, std::vector<double> (nx, -INFINITY));
+  std::vector<double> qc (nC, 0.0);
   *loglike_sum = 0;
-  for (size_t y = 0; y < ny; ++y) {
+  // the reference's per-read replay (qmodel.cpp:2247-2270) over the pairs [first[y], first[y+1]) of read y: the
+  // order-dependent gate "F >= yLL - 20", the running yLL, the posterior weights of the gated pairs and the new sortOrder
+  auto replay_read = [&] (size_t y, const double* Fy, double* wy, std::vector<size_t>* gated_out) {
     double yLL = use_null ? null_loglike[y] : -INFINITY;
     std::vector<size_t> gated;
-    for (size_t p = first[y]; p < first[y + 1]; ++p) {
-      xyLL[y][xi[p]] = F[p];
-      if (F[p] >= yLL - 20) gated.push_back (p);                  // MAX_TRAINING_LOG_DELTA, qmodel.cpp:23, 2252
-      yLL = qg_host_lse (tab, yLL, F[p]);
+    const size_t n = first[y + 1] - first[y];
+    for (size_t t = 0; t < n; ++t) {
+      xyLL[y][xi[first[y] + t]] = Fy[t];
+      if (Fy[t] >= yLL - 20) gated.push_back (t);                 // MAX_TRAINING_LOG_DELTA, qmodel.cpp:23, 2252
+      yLL = qg_host_lse (tab, yLL, Fy[t]);
     }
-    for (size_t p : gated) { bxi.push_back (xi[p]); byi.push_back ((uint32_t) y); bw.push_back (exp (F[p] - yLL)); bpick.push_back (p); }
+    if (wy) { for (size_t t = 0; t < n; ++t) wy[t] = 0.0; for (size_t t : gated) wy[t] = exp (Fy[t] - yLL); }
+    if (gated_out) for (size_t t : gated) gated_out->push_back (first[y] + t);
     y_loglike[y] = yLL;
-    *loglike_sum += yLL;                                          // accumulate(yLogLike, 0.), qmodel.cpp:2420-2422
     // sortOrder := refs by descending F, cut at the first one below yLL - 20 (qmodel.cpp:2264-2270)
     std::vector<size_t> idx (nx);
     std::iota (idx.begin (), idx.end (), (size_t) 0);
@@ -1887,17 +1920,56 @@ extern "C" int qg_estep (qg_ctx* ctx, const qg_dpconfig* cfg, int use_null, cons
     uint32_t len = 0;
     for (size_t t = nx; t-- > 0; ) { if (v[idx[t]] < yLL - 20) break; sort_order[y * nx + len++] = (uint32_t) idx[t]; }
     sort_len[y] = len;
-  }
+  };
 
-  // 3. Backward on the gated pairs, posterior-weighted sum of QuaffCounts, then QuaffParamCounts (qmodel.cpp:407-417)
-  std::vector<double> qc (nC, 0.0);
-  if (!bxi.empty ()) {
-    const bool reuse = env_all.run_begin.size () == xi.size () + 1 && !getenv ("QG_ESTEP_RESEED");
-    if (reuse) { g_env_reuse.src = &env_all; g_env_reuse.pick = &bpick; }
-    const int rc = qg_backward_counts (ctx, cfg, bxi.size (), bxi.data (), byi.data (), bw.data (), nullptr, nullptr, qc.data (), nullptr);
-    g_env_reuse.src = nullptr; g_env_reuse.pick = nullptr;
-    QG_TRY (rc);
+  // 1+3 in one pass (default): Forward with the cells kept and Backward for EVERY pair of a memory batch, the posterior
+  // weights computed from the batch's Forward results while its Backward runs; pairs that fail the gate get weight 0
+  // (they are the wrong-strand pairs: a handful of narrow runs each, so filling them backwards costs little, whereas
+  // the two-pass form filled the right-strand pairs forwards twice)
+  bool done = false;
+  if (!xi.empty () && cfg->sparse && !getenv ("QG_ESTEP_TWO_PASS")) {
+    qg_weight_hook hook;
+    hook.group_first = &first;
+    hook.fn = [&] (size_t p0, size_t p1, const double* fwd, double* w) {
+      // a batch is a range of whole reads: first[y] >= p0 for its first read
+      for (size_t y = std::lower_bound (first.begin (), first.end (), p0) - first.begin (); y < ny && first[y] < p1; ++y)
+        if (first[y + 1] > first[y]) replay_read (y, fwd + (first[y] - p0), w + (first[y] - p0), nullptr);
+    };
+    g_weight_hook = &hook;
+    const int rc = qg_backward_counts (ctx, cfg, xi.size (), xi.data (), yi.data (), nullptr, F.data (), nullptr, qc.data (), nullptr);
+    g_weight_hook = nullptr;
+    if (rc == QG_OK) {
+      done = true;
+      for (size_t y = 0; y < ny; ++y) if (first[y] == first[y + 1]) replay_read (y, nullptr, nullptr, nullptr);   // reads without pairs
+    } else if (rc != QG_RETRY_TWO_PASS) return rc;
+    else std::fill (qc.begin (), qc.end (), 0.0);
   }
+  if (!done) {
+    // two passes: Forward for every (read, ref in sortOrder) pair, the replay, then Forward + Backward of the gated pairs
+    qg_env_result env_all;                                         // the Forward pass's envelopes, reused by the Backward pass
+    if (!xi.empty ()) {
+      g_env_reuse.keep = &env_all;
+      const int rc = qg_forward (ctx, cfg, xi.size (), xi.data (), yi.data (), F.data ());
+      g_env_reuse.keep = nullptr;
+      QG_TRY (rc);
+    }
+    std::vector<uint32_t> bxi, byi; std::vector<double> bw; std::vector<size_t> bpick;
+    std::vector<double> wtmp;
+    for (size_t y = 0; y < ny; ++y) {
+      const size_t before = bpick.size ();
+      wtmp.assign (first[y + 1] - first[y], 0.0);
+      replay_read (y, F.data () + first[y], wtmp.data (), &bpick);
+      for (size_t q = before; q < bpick.size (); ++q) { const size_t p = bpick[q]; bxi.push_back (xi[p]); byi.push_back ((uint32_t) y); bw.push_back (wtmp[p - first[y]]); }
+    }
+    if (!bxi.empty ()) {
+      const bool reuse = env_all.run_begin.size () == xi.size () + 1 && !getenv ("QG_ESTEP_RESEED");
+      if (reuse) { g_env_reuse.src = &env_all; g_env_reuse.pick = &bpick; }
+      const int rc = qg_backward_counts (ctx, cfg, bxi.size (), bxi.data (), byi.data (), bw.data (), nullptr, nullptr, qc.data (), nullptr);
+      g_env_reuse.src = nullptr; g_env_reuse.pick = nullptr;
+      QG_TRY (rc);
+    }
+  }
+  for (size_t y = 0; y < ny; ++y) *loglike_sum += y_loglike[y];      // accumulate(yLogLike, 0.), qmodel.cpp:2420-2422
   const size_t nEmit = 4 * nK * QG_NQUAL + 4 * QG_NQUAL;
   memcpy (param_counts, qc.data (), sizeof (double) * nEmit);
   const double *m2m = qc.data () + nEmit, *m2i = m2m + nG, *m2d = m2i + nG, *m2e = m2d + nG, *sc = m2e + nG;
