@@ -9,12 +9,23 @@
 #include <cmath>
 #include <map>
 #include <mutex>
+#include <thread>
 #include "qmodel.h"
 #include "qoverlap.h"
 #include "quaffgpu.h"
 
 int quaffGpuDevice = -1;
 std::vector<int> quaffGpuDevices;                 // -gpu 0,1,2,3 / -gpu all: the reads shard over these devices
+
+namespace {
+std::thread gpuWarmThread;
+}
+void quaffGpuWarmStart () {
+  if (gpuWarmThread.joinable() || getenv ("QUAFF_GPU_NO_WARM_START")) return;
+  const std::vector<int> devs = quaffGpuDevices;
+  gpuWarmThread = std::thread ([devs] { qg_init_devices (devs.data(), (int) devs.size()); });   // errors resurface in qg_create
+}
+void quaffGpuWarmJoin () { if (gpuWarmThread.joinable()) gpuWarmThread.join(); }
 
 // -gpu [device | device,device,... | all]
 bool quaffGpuParseArg (std::deque<std::string>& argvec) {
@@ -34,6 +45,9 @@ bool quaffGpuParseArg (std::deque<std::string>& argvec) {
     }
     if (quaffGpuDevices.empty()) quaffGpuDevices.push_back (0);
     quaffGpuDevice = quaffGpuDevices[0];
+    // the devices are known before any sequence file has been read: initialise them on a side thread while the
+    // reference's loader parses FASTA / FASTQ (joined by the seams before they create their contexts)
+    quaffGpuWarmStart();
     return true;
   }
   return false;
@@ -74,7 +88,7 @@ Flat flatten (const vguard<FastSeq>& seqs, bool wantQual) {
 
 struct Gpu {
   qg_ctx* ctx;
-  Gpu () : ctx (NULL) { Require (qg_create (&ctx, quaffGpuDevice) == QG_OK, "-gpu: %s", qg_last_error (NULL)); }
+  Gpu () : ctx (NULL) { quaffGpuWarmJoin(); Require (qg_create (&ctx, quaffGpuDevice) == QG_OK, "-gpu: %s", qg_last_error (NULL)); }
   ~Gpu () { qg_destroy (ctx); }
   void ok (int rc) const { Require (rc == QG_OK, "-gpu: %s", qg_last_error (ctx)); }
 };
@@ -94,6 +108,7 @@ struct GpuPool {
   qg_pool* pool;
   GpuPool (int perDevice) : pool (NULL) {
     if (quaffGpuDevices.empty()) quaffGpuDevices.push_back (quaffGpuDevice);
+    quaffGpuWarmJoin();
     Require (qg_pool_create (&pool, quaffGpuDevices.data(), (int) quaffGpuDevices.size(), perDevice) == QG_OK, "-gpu: %s", qg_pool_last_error (NULL));
   }
   ~GpuPool () { qg_pool_destroy (pool); }

@@ -201,6 +201,9 @@ int qg_overlap_reads (qg_ctx* ctx, const qg_dpconfig* cfg, size_t n_originals, c
  * (qmodel.cpp:2650-2668 for align, qmodel.cpp:2013-2029 for the E-step).                                  */
 typedef struct qg_pool qg_pool;
 int  qg_device_count (void);
+/* blocking: driver + primary-context initialisation of the listed devices (seconds on a multi-GPU box); meant to be called
+ * from a side thread while the host is still reading its inputs, so that qg_create / qg_pool_create find them ready   */
+int  qg_init_devices (const int* devices, int n_devices);
 int  qg_pool_create (qg_pool** out, const int* devices, int n_devices, int contexts_per_device);
 void qg_pool_destroy (qg_pool* pool);
 const char* qg_pool_last_error (const qg_pool* pool);     /* pool may be NULL: last qg_pool_create failure */

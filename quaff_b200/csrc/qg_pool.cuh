@@ -28,6 +28,17 @@ extern "C" int qg_device_count (void) {
   return n;
 }
 
+// The first touch of a device (driver initialisation + primary context) costs seconds on a multi-GPU box.  A host that knows
+// early which devices it will use (the CLI does, from its flags) calls this from a side thread while it still parses its
+// inputs; the later qg_create / qg_pool_create find the devices ready.
+extern "C" int qg_init_devices (const int* devices, int n_devices) {
+  if (!devices || n_devices < 1) return QG_ERR_INVALID;
+  for (int d = 0; d < n_devices; ++d) {
+    if (cudaSetDevice (devices[d]) != cudaSuccess || cudaFree (0) != cudaSuccess) { cudaGetLastError (); return QG_ERR_NO_DEVICE; }
+  }
+  return QG_OK;
+}
+
 extern "C" int qg_pool_create (qg_pool** out, const int* devices, int n_devices, int contexts_per_device) {
   if (!out || n_devices < 1 || contexts_per_device < 1 || !devices) return QG_ERR_INVALID;
   *out = nullptr;
