@@ -33,9 +33,12 @@ extern "C" int qg_device_count (void) {
 // inputs; the later qg_create / qg_pool_create find the devices ready.
 extern "C" int qg_init_devices (const int* devices, int n_devices) {
   if (!devices || n_devices < 1) return QG_ERR_INVALID;
-  for (int d = 0; d < n_devices; ++d) {
-    if (cudaSetDevice (devices[d]) != cudaSuccess || cudaFree (0) != cudaSuccess) { cudaGetLastError (); return QG_ERR_NO_DEVICE; }
-  }
+  std::vector<int> rc (n_devices, QG_OK);
+  std::vector<std::thread> th;
+  for (int d = 0; d < n_devices; ++d)                        // one thread per device: the primary contexts are created concurrently
+    th.emplace_back ([&, d] { if (cudaSetDevice (devices[d]) != cudaSuccess || cudaFree (0) != cudaSuccess) { cudaGetLastError (); rc[d] = QG_ERR_NO_DEVICE; } });
+  for (auto& t : th) t.join ();
+  for (int d = 0; d < n_devices; ++d) if (rc[d] != QG_OK) return rc[d];
   return QG_OK;
 }
 

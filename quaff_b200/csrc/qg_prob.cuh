@@ -189,7 +189,7 @@ qg_forward_prob_kernel (const qg_prob_args a) {
         a.endex[sg.aux_off + s0 + c] = ex;
       }
     }
-    if (a.do_store && active) {
+    if (a.do_store && active && s0 < width) {                 // lanes beyond the run hold padding only (a 65-diagonal band uses 22 of 32 lanes): nothing to keep
       // skewed layout [macro-step][lane][state][c] (see qg_dp.cuh); exponents [macro-step][lane]
       double* st = a.store + sg.store_off + ((uint64_t) u * 32 + lane) * (3 * R);
 #pragma unroll
@@ -360,19 +360,20 @@ qg_backward_prob_kernel (const qg_prob_args a) {
   // its macro-step yLen + 32 - u) is fetched one macro-step ahead: a warp is one long dependent chain and there are
   // few warps per SM, so an HBM round trip per step would otherwise be fully exposed
   double pf[3 * R]; int pfex;
+  const bool fkept = R * flane < width;                       // the Forward lane wrote its records only if it owns real diagonals
   {
     const uint64_t fr = (uint64_t) (ylen + 32 - 1) * 32 + flane;
     const double* s1 = stbase + fr * (3 * R);
 #pragma unroll
-    for (int t = 0; t < 3 * R; ++t) pf[t] = s1[t];
-    pfex = stex[fr];
+    for (int t = 0; t < 3 * R; ++t) pf[t] = fkept ? s1[t] : 0.0;
+    pfex = fkept ? stex[fr] : 0;
   }
   for (int u = 1; u <= total; ++u) {
     double st[3 * R];
 #pragma unroll
     for (int t = 0; t < 3 * R; ++t) st[t] = pf[t];
     const int stex_cur = pfex;
-    if (u < total) {
+    if (u < total && fkept) {
       const uint64_t fr = (uint64_t) (ylen + 32 - (u + 1)) * 32 + flane;
       const double* s1 = stbase + fr * (3 * R);
 #pragma unroll
