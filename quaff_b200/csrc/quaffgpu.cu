@@ -1494,9 +1494,11 @@ static bool qg_plan_single_warp (const qg_dp_plan& plan) {
 static int qg_stage_rowq (qg_ctx* ctx, const qg_dp_plan& plan) {
   QG_TRY (qg_reserve (ctx, ctx->scratch[SC_RQ], sizeof (qg_rowq) * (plan.rp_rows + 1)));
   QG_TRY (qg_reserve (ctx, ctx->scratch[SC_RS], sizeof (double) * (plan.rp_rows + 1)));
+  QG_TRY (qg_reserve (ctx, ctx->scratch[SC_RPS], sizeof (qg_rowq) * (plan.rp_rows + 1)));     // structure-of-arrays copy (the Viterbi kernels' slot: not live in a Forward / Backward call)
   if (!plan.rp_jobs.empty ()) {
     QG_LAUNCH (qg_rowq_kernel, (unsigned) plan.rp_jobs.size (), 256, 0, ctx->stream,
-               ctx->scratch[SC_RPJOBS].as<qg_rp_job> (), ctx->scratch[SC_RP].as<qg_rowp> (), ctx->scratch[SC_RQ].as<qg_rowq> (), ctx->scratch[SC_RS].as<double> ());
+               ctx->scratch[SC_RPJOBS].as<qg_rp_job> (), ctx->scratch[SC_RP].as<qg_rowp> (), ctx->scratch[SC_RQ].as<qg_rowq> (), ctx->scratch[SC_RS].as<double> (),
+               ctx->scratch[SC_RPS].as<double2> ());
     QG_TRY (qg_check_launch (ctx, "qg_rowq_kernel"));
   }
   return QG_OK;
@@ -1508,6 +1510,7 @@ static qg_prob_args qg_prob_base_args (qg_ctx* ctx, const qg_dpconfig* cfg, int 
   a.xpacked = ctx->seqs[x_set].d_packed.as<uint64_t> ();
   a.xpoff = ctx->seqs[x_set].d_poff.as<uint64_t> ();
   a.rq = ctx->scratch[SC_RQ].as<qg_rowq> ();
+  a.rqs = ctx->scratch[SC_RPS].as<double2> ();
   a.rs = ctx->scratch[SC_RS].as<double> ();
   a.pi2i = exp (ctx->model.i2i); a.pi2m = exp (ctx->model.i2m); a.pd2d = exp (ctx->model.d2d); a.pd2m = exp (ctx->model.d2m);
   a.local = cfg->local;
