@@ -207,17 +207,20 @@ def run_cli(args):
     if not os.path.exists(GPU_QUAFF):
         print(json.dumps({"metric": "align_reads_per_sec_cli", "unavailable": "host/_build/quaff-gpu not built (needs the reference sources at build time)"}), flush=True)
         return
-    n_reads = args.reads_per_step if args.reads_per_step != READS_PER_STEP else 12288
+    n_distinct = args.reads_per_step if args.reads_per_step != READS_PER_STEP else 12288
+    copies = int(os.environ.get("QB_CLI_COPIES", "4"))          # the read file = `copies` renamed copies of the distinct reads (synthesis is the slow part of this bench)
+    n_reads = n_distinct * copies
     ref = random_ref(args.ref_len, 1)
-    reads, _, _ = sample_reads(ref, n_reads, args.read_len, 2, name_prefix="r0b0_")
+    reads, _, _ = sample_reads(ref, n_distinct, args.read_len, 2, name_prefix="r0b0_")
     devs = ",".join(str(d) for d in range(args.gpus))
     with tempfile.TemporaryDirectory() as td:
         fa, fq, fq2 = os.path.join(td, "ref.fa"), os.path.join(td, "reads.fq"), os.path.join(td, "two.fq")
         with open(fa, "w") as fh:
             fh.write(f">{ref.name}\n{ref.seq}\n")
         with open(fq, "w") as fh:
-            for r in reads:
-                fh.write(f"@{r.name}\n{r.seq}\n+\n{r.qual}\n")
+            for cp in range(copies):
+                for r in reads:
+                    fh.write(f"@{r.name}{'' if cp == 0 else '_copy%d' % cp}\n{r.seq}\n+\n{r.qual}\n")
         with open(fq2, "w") as fh:
             for r in reads[:2]:
                 fh.write(f"@{r.name}\n{r.seq}\n+\n{r.qual}\n")
@@ -254,7 +257,7 @@ def run_cli(args):
         "metric": "align_reads_per_sec_cli", "value": n_reads / dt, "unit": "reads/s", "n_gpus": args.gpus, "steps": len(times), "warmup": max(1, args.warmup // 3),
         "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": CFG4_WORKLOAD + "; through the reference CLI with -gpu (host/_build/quaff-gpu), FASTQ in, SAM out",
-                   "reads": n_reads, "ref_len": args.ref_len, "read_len": args.read_len, "devices": devs,
+                   "reads": n_reads, "distinct_reads": n_distinct, "ref_len": args.ref_len, "read_len": args.read_len, "devices": devs,
                    "fastq_bytes": fq_bytes, "sam_bytes": sam_bytes, "sam_records": n_sam},
         "e2e": {"value": n_reads / dt, "unit": "reads/s", "h2d_bytes_per_step": None, "d2h_bytes_per_step": None,
                 "note": "wall clock of the whole process, exec to exit"},

@@ -2,6 +2,8 @@
 // QuaffTrainer::getCounts qmodel.cpp:2005) routed to libquaffgpu.  The reference keeps everything else: flag parsing,
 // sequence loading, params / null model, the Alignment type and every output writer.
 #include <time.h>
+#include <zlib.h>
+#include <ctype.h>
 #include <cstdio>
 #include <fstream>
 #include <sstream>
@@ -10,6 +12,8 @@
 #include <map>
 #include <mutex>
 #include <thread>
+#include <future>
+#include <memory>
 #include "qmodel.h"
 #include "qoverlap.h"
 #include "quaffgpu.h"
@@ -18,14 +22,18 @@ int quaffGpuDevice = -1;
 std::vector<int> quaffGpuDevices;                 // -gpu 0,1,2,3 / -gpu all: the reads shard over these devices
 
 namespace {
-std::thread gpuWarmThread;
+std::shared_future<void> gpuWarmDone;                      // detached worker: an error exit of the CLI must not trip over a joinable thread
+bool gpuWarmStarted = false;
 }
 void quaffGpuWarmStart () {
-  if (gpuWarmThread.joinable() || getenv ("QUAFF_GPU_NO_WARM_START")) return;
+  if (gpuWarmStarted || getenv ("QUAFF_GPU_NO_WARM_START")) return;
+  gpuWarmStarted = true;
   const std::vector<int> devs = quaffGpuDevices;
-  gpuWarmThread = std::thread ([devs] { qg_init_devices (devs.data(), (int) devs.size()); });   // errors resurface in qg_create
+  std::shared_ptr<std::promise<void> > done (new std::promise<void>);
+  gpuWarmDone = done->get_future().share();
+  std::thread ([devs, done] { qg_init_devices (devs.data(), (int) devs.size()); done->set_value(); }).detach();   // errors resurface in qg_create
 }
-void quaffGpuWarmJoin () { if (gpuWarmThread.joinable()) gpuWarmThread.join(); }
+void quaffGpuWarmJoin () { if (gpuWarmStarted && gpuWarmDone.valid()) gpuWarmDone.wait(); }
 
 // -gpu [device | device,device,... | all]
 bool quaffGpuParseArg (std::deque<std::string>& argvec) {
@@ -227,6 +235,118 @@ void writeSamRecord (std::ostream& out, const FastSeq& x, const FastSeq& y, uint
   out << s1.name << '\t' << flag << '\t' << s0.name << '\t' << s0.start << "\t0\t" << cigar << "\t*\t0\t0\t*\t*\tAS:i:" << ((int) round (score)) << endl;
 }
 }  // namespace
+
+// ---- ingest --------------------------------------------------------------------------------------------
+// readFastSeqs (fastseq.cpp:148-176) with -gpu: the reference reads through kseq one character at a time from a 4 KB buffer
+// (~95 MB/s: at GPU speed the loader is the slowest stage of `quaff align`).  Here the file is inflated / read in 4 MB pieces
+// into memory and parsed in place by the same state machine as kseq_read (kseq/kseq.h:169-207) -- header character, name up to
+// the first whitespace, comment up to the end of the line, sequence = printable characters up to the next '>', '+' or '@',
+// then for FASTQ the rest of the '+' line and quality characters 33..127 until the sequence length is reached (one more
+// character is consumed, as kseq does) -- so multi-line records, missing qualities and truncated files give the same FastSeq
+// vector.  filepos is what gztell returned to the reference before each record: the end of the last 4 KB block kseq had read.
+vguard<FastSeq> quaffGpuReadFastSeqs (const char* filename) {
+  vguard<FastSeq> seqs;
+  // the whole file in memory: read(2) for plain files, zlib for gzip (magic 1f 8b); no zero-filled growth
+  struct Buf { char* p; size_t n, cap; Buf () : p (NULL), n (0), cap (0) { } ~Buf () { free (p); }
+               void room (size_t more) { if (n + more > cap) { cap = std::max (cap * 2, n + more); p = (char*) realloc (p, cap); Require (p != NULL, "out of memory reading sequences"); } } } data;
+  {
+    FILE* raw = fopen (filename, "rb");
+    Require (raw != NULL, "Couldn't open %s", filename);
+    unsigned char magic[2] = {0, 0};
+    const size_t got2 = fread (magic, 1, 2, raw);
+    const bool gz = got2 == 2 && magic[0] == 0x1f && magic[1] == 0x8b;
+    if (!gz) {
+      rewind (raw);
+      const size_t piece = 8u << 20;
+      for (;;) { data.room (piece); const size_t got = fread (data.p + data.n, 1, piece, raw); if (got == 0) break; data.n += got; }
+      fclose (raw);
+    } else {
+      fclose (raw);
+      gzFile fp = gzopen (filename, "r");
+      Require (fp != Z_NULL, "Couldn't open %s", filename);
+      gzbuffer (fp, 1 << 20);
+      const size_t piece = 4u << 20;
+      for (;;) { data.room (piece); const int got = gzread (fp, data.p + data.n, (unsigned) piece); if (got <= 0) break; data.n += (size_t) got; }
+      gzclose (fp);
+    }
+  }
+  // character classes of kseq_read: separators of the name (isspace), sequence characters (isgraph and not a record marker)
+  bool isSpace[256], isSeq[256];
+  for (int c = 0; c < 256; ++c) { isSpace[c] = isspace (c) != 0; isSeq[c] = isgraph (c) != 0 && c != '>' && c != '+' && c != '@' && c < 128; }
+  const char* d = data.p;
+  const size_t n = data.n;
+  size_t pos = 0;                                          // next unread byte
+  int lastChar = 0;
+  const std::string fname (filename);
+  for (;;) {
+    const size_t blocks = (pos + 4095) / 4096;
+    const z_off_t filepos = (z_off_t) std::min<size_t> (n, blocks * 4096);
+    // kseq_read
+    if (lastChar == 0) {
+      while (pos < n && d[pos] != '>' && d[pos] != '@') ++pos;
+      if (pos >= n) break;
+      lastChar = d[pos++];
+    }
+    if (pos >= n) break;                                   // ks_getuntil on an exhausted stream: -1
+    FastSeq fs;
+    int c = 0;
+    {
+      size_t e = pos;
+      while (e < n && !isSpace[(unsigned char) d[e]]) ++e;
+      fs.name.assign (d + pos, strnlen (d + pos, e - pos));                // string(ks->name.s): up to the first NUL
+      if (e < n) { c = d[e]; pos = e + 1; } else { c = 0; pos = n; }
+    }
+    if (c != '\n') {
+      size_t e = pos;
+      while (e < n && d[e] != '\n') ++e;
+      if (e > pos) fs.comment.assign (d + pos, strnlen (d + pos, e - pos));
+      pos = e < n ? e + 1 : n;
+    }
+    std::string& sq = fs.seq;
+    c = -1;
+    while (pos < n) {
+      size_t e = pos;                                      // a run of sequence characters (whole lines in practice)
+      while (e < n && isSeq[(unsigned char) d[e]]) ++e;
+      sq.append (d + pos, e - pos);
+      pos = e;
+      if (pos >= n) break;
+      const int t = (unsigned char) d[pos++];
+      if (t == '>' || t == '+' || t == '@') { c = t; break; }       // otherwise a separator (newline, blank, control character): skipped
+    }
+    if (c == '>' || c == '@') lastChar = c;
+    { const size_t z = sq.find ('\0'); if (z != std::string::npos) sq.resize (z); }      // string(ks->seq.s)
+    bool haveQual = false;
+    if (c == '+') {
+      while (pos < n && d[pos] != '\n') ++pos;
+      if (pos < n) {
+        ++pos;
+        std::string ql;
+        ql.reserve (sq.size());
+        const size_t want = fs.seq.size();                 // kseq counts the raw sequence length; a NUL inside a sequence is not a case worth keeping apart
+        while (pos < n && ql.size() < want) {
+          size_t e = pos;                                  // a run of quality characters, at most what is still missing
+          const size_t lim = std::min (n, pos + (want - ql.size()));
+          while (e < lim && (unsigned char) d[e] >= 33 && (unsigned char) d[e] <= 127) ++e;
+          ql.append (d + pos, e - pos);
+          pos = e;
+          if (ql.size() < want && pos < n) ++pos;          // a character outside 33..127 (the newline of a multi-line record): skipped
+        }
+        if (pos < n && ql.size() >= want) ++pos;           // kseq reads one more character before it notices the quality string is complete
+        lastChar = 0;
+        haveQual = ql.size() == want;
+        if (haveQual) fs.qual.swap (ql);
+      } else lastChar = 0;                                  // truncated after '+': kseq returns -2, the record is kept without qualities
+    }
+    fs.filename = fname;
+    fs.filepos = filepos;
+    seqs.push_back (FastSeq());
+    std::swap (seqs.back(), fs);
+  }
+  LogThisAt(3, "Read " << plural(seqs.size(),"sequence") << " from " << filename << endl);
+  if (seqs.empty())
+    Warn ("Couldn't read any sequences from %s", filename);
+  return seqs;
+}
 
 // ---- seam A -------------------------------------------------------------------------------------------------------
 namespace {

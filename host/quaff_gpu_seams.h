@@ -17,6 +17,8 @@ template<typename T> class vguard;
 extern int quaffGpuDevice;                       // -1 = CPU path (default); >= 0 = CUDA device used by the three seams
 bool quaffGpuParseArg (std::deque<std::string>& argvec);     // consumes "-gpu [device | device,device,... | all]"
 
+void quaffGpuWarmStart ();
+vguard<FastSeq> quaffGpuReadFastSeqs (const char* filename);   // readFastSeqs (fastseq.cpp:148) at memory speed, same records
 void quaffGpuAlign (QuaffAligner& aligner, std::ostream& out, const vguard<FastSeq>& x, const vguard<FastSeq>& y,
                     const QuaffParams& params, const QuaffNullParams& nullModel, QuaffDPConfig& config);
 void quaffGpuOverlap (QuaffOverlapAligner& aligner, std::ostream& out, const vguard<FastSeq>& seqs, size_t nOriginals,

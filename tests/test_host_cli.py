@@ -138,3 +138,48 @@ def test_cli_reference_golden_files(tmp_path):
     assert json.loads(out) == g["counts"]
     out = _run(GPUQ, ["count", c8, c8, "-kmatchmb", "10", "-fwdstrand", "-gpu"])
     assert json.loads(out) == g["counts"]
+
+
+def test_loader_matches_reference(tmp_path):
+    """the -gpu loader (host/quaff_gpu_seams.cpp: quaffGpuReadFastSeqs) returns the reference's FastSeq vector --
+    names, comments, sequences, qualities, file positions -- for FASTA / FASTQ, plain and gzipped, multi-line records, comments,
+    quality lines that start with '@' or '+', blank lines, a truncated last record and a file without records"""
+    import gzip
+    import random
+    loader = os.path.join(ROOT, "host", "_build", "loader-test")
+    if not os.path.isdir("/root/reference/src") and not os.path.exists(loader):
+        pytest.skip("host/_build/loader-test is built where the reference sources exist")
+    if os.path.isdir("/root/reference/src"):
+        subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "host"), "all", "loader-test"], check=True, timeout=900)
+    rng = random.Random(7)
+    rnd = lambda n: "".join(rng.choice("ACGT") for _ in range(n))
+    qs = lambda n: "".join(chr(rng.randint(33, 126)) for _ in range(n))
+    files = []
+    p = tmp_path / "a.fa"; files.append(p)
+    s = rnd(700)
+    p.write_text(">ref1 some comment here\n" + "".join(s[i:i + 60] + "\n" for i in range(0, 700, 60)) + ">ref2\n" + rnd(300) + "\n\n>ref3\tt\n" + rnd(123) + "\n>c\n" + rnd(9000))
+    p = tmp_path / "b.fq"; files.append(p)
+    with open(p, "w") as f:
+        for k in range(300):
+            n = rng.randint(1, 300); sq = rnd(n); ql = qs(n)
+            if k % 7 == 0: sq = sq.lower()
+            if k % 5 == 0: ql = "@" + ql[1:]
+            if k % 11 == 0: ql = "+" + ql[1:]
+            f.write(f"@r{k}\tcomment {k}  with  spaces\n{sq}\n+r{k}\n{ql}\n")
+            if k % 13 == 0: f.write("\n")
+        f.write("@last\n" + rnd(200) + "\n+last\n" + qs(150))              # truncated quality string
+    p = tmp_path / "c.fq.gz"; files.append(p)
+    with gzip.open(p, "wt") as f:
+        for k in range(30):
+            n = rng.randint(5000, 9000); f.write(f"@g{k}\n{rnd(n)}\n+\n{qs(n)}\n")
+    p = tmp_path / "f.fq"; files.append(p)
+    with open(p, "w") as f:                                                   # multi-line FASTQ
+        for k in range(20):
+            n = rng.randint(100, 900); sq = rnd(n); ql = qs(n).replace("@", "A").replace("+", "B")
+            f.write(f"@m{k}\n" + "".join(sq[i:i + 80] + "\n" for i in range(0, n, 80)) + "+\n" + "".join(ql[i:i + 80] + "\n" for i in range(0, n, 80)))
+    p = tmp_path / "g.txt"; files.append(p)
+    p.write_text("no records here\n")
+    gold = os.path.join(ROOT, "tests", "golden")
+    files += [os.path.join(gold, "c8f30.fastq.gz"), os.path.join(gold, "tiny.fasta"), os.path.join(gold, "tiny.fastq")]
+    res = subprocess.run([loader] + [str(f) for f in files], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
+    assert res.returncode == 0 and res.stdout.count("identical") == len(files), res.stdout + res.stderr[-500:]
