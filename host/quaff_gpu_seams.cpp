@@ -62,6 +62,16 @@ bool quaffGpuParseArg (std::deque<std::string>& argvec) {
 }
 
 namespace {
+// [0, n) in contiguous ranges over the host's cores (tokenising and the null model are per-read work)
+template<class F>
+void parallelRanges (size_t n, F fn) {
+  size_t nt = std::min<size_t> (std::max (1u, std::thread::hardware_concurrency()), 16);
+  if (n < 256 || nt < 2) { fn ((size_t) 0, n); return; }
+  std::vector<std::thread> th;
+  for (size_t t = 0; t < nt; ++t) { const size_t a = n * t / nt, b = n * (t + 1) / nt; if (a < b) th.emplace_back ([=] { fn (a, b); }); }
+  for (auto& x : th) x.join();
+}
+
 struct Flat { std::vector<uint8_t> tok, qual; std::vector<uint64_t> off; bool quals; };
 
 // FastSeq::tokens / FastSeq::qualScores (fastseq.cpp:71-83, 101-109) for a whole set into flat arrays, through 256-entry
@@ -80,17 +90,22 @@ Flat flatten (const vguard<FastSeq>& seqs, bool wantQual) {
   for (size_t n = 0; n < seqs.size(); ++n) f.off[n+1] = f.off[n] + seqs[n].length();
   f.tok.resize (f.off.back());
   if (f.quals) f.qual.resize (f.off.back());
-  for (size_t n = 0; n < seqs.size(); ++n) {
-    const FastSeq& s = seqs[n];
-    uint8_t* t = f.tok.data() + f.off[n];
-    const size_t len = s.length();
-    for (size_t i = 0; i < len; ++i) {
-      const int v = tokOf[(unsigned char) s.seq[i]];
-      if (v < 0) { cerr << "Unknown symbol " << s.seq[i] << " in sequence " << s.name << endl; throw; }
-      t[i] = (uint8_t) v;
+  const std::string* bad = NULL; char badChar = 0;
+  std::mutex badMx;
+  parallelRanges (seqs.size(), [&] (size_t n0, size_t n1) {
+    for (size_t n = n0; n < n1; ++n) {
+      const FastSeq& s = seqs[n];
+      uint8_t* t = f.tok.data() + f.off[n];
+      const size_t len = s.length();
+      for (size_t i = 0; i < len; ++i) {
+        const int v = tokOf[(unsigned char) s.seq[i]];
+        if (v < 0) { std::lock_guard<std::mutex> lock (badMx); if (!bad || &s.name < bad) { bad = &s.name; badChar = s.seq[i]; } return; }
+        t[i] = (uint8_t) v;
+      }
+      if (f.quals) { uint8_t* q = f.qual.data() + f.off[n]; for (size_t i = 0; i < len; ++i) q[i] = qualOf[(unsigned char) s.qual[i]]; }
     }
-    if (f.quals) { uint8_t* q = f.qual.data() + f.off[n]; for (size_t i = 0; i < len; ++i) q[i] = qualOf[(unsigned char) s.qual[i]]; }
-  }
+  });
+  if (bad) { cerr << "Unknown symbol " << badChar << " in sequence " << *bad << endl; throw; }      // FastSeq::tokens, fastseq.cpp:76-79
   return f;
 }
 
@@ -154,8 +169,10 @@ std::vector<double> nullLogLikes (const QuaffNullParams& nullModel, const Flat& 
   double pqr[12];
   for (int t = 0; t < 4; ++t) { pqr[3*t] = nullModel.null[t].symProb; pqr[3*t+1] = nullModel.null[t].qualTrialSuccessProb; pqr[3*t+2] = nullModel.null[t].qualNumSuccessfulTrials; }
   std::vector<double> ll (seqs.size());
-  for (size_t n = 0; n < seqs.size(); ++n)
-    ll[n] = qg_null_loglike (nullModel.nullEmit, pqr, f.tok.data() + f.off[n], seqs[n].hasQual() ? f.qual.data() + f.off[n] : NULL, f.off[n+1] - f.off[n]);
+  parallelRanges (seqs.size(), [&] (size_t n0, size_t n1) {
+    for (size_t n = n0; n < n1; ++n)
+      ll[n] = qg_null_loglike (nullModel.nullEmit, pqr, f.tok.data() + f.off[n], seqs[n].hasQual() ? f.qual.data() + f.off[n] : NULL, f.off[n+1] - f.off[n]);
+  });
   return ll;
 }
 
