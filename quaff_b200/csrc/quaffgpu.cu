@@ -942,6 +942,15 @@ static bool qg_pair_is_wide (const qg_env_result& er, size_t p) {
   return false;
 }
 
+// a run of more than 256 diagonals needs several warps: the probability-space Forward / Backward kernels are single-warp, such
+// pairs take the log-space kernels.  The choice is a function of the pair alone (not of its batch-mates): a call that holds
+// both kinds is split and each part served by its kernels.
+static bool qg_pair_is_multiwarp (const qg_env_result& er, size_t p) {
+  for (uint32_t r = er.run_begin[p]; r < er.run_begin[p + 1]; ++r)
+    if ((uint32_t) (er.runs[r].y - er.runs[r].x + 1) > 256u) return true;
+  return false;
+}
+
 // mode 0: Viterbi (+ traceback of the pairs flagged in want); mode 1: Forward log-likelihood.  idx: the wide pairs'
 // positions in the caller's pair list; outputs are written at those positions.
 // mode 2: Forward with every cell kept, Backward + counts (qg_tile_backward_kernel); fb carries its inputs and outputs.
@@ -1557,13 +1566,35 @@ extern "C" int qg_forward (qg_ctx* ctx, const qg_dpconfig* cfg, size_t n_pairs, 
     for (size_t p = 0; p < n_pairs; ++p) (qg_pair_is_wide (er, p) ? wide : narrow).push_back (p);
     if (!wide.empty ()) {
       QG_TRY (qg_wide_run (ctx, cfg, er, wide, xi, yi, 1, nullptr, loglike, nullptr, nullptr, nullptr));
-      if (!narrow.empty ()) {                               // the rest through the ordinary path (their envelopes are recomputed: rare, mixed calls only)
+      if (!narrow.empty ()) {                               // the rest through the ordinary path, with the envelopes already computed
         std::vector<uint32_t> sxi, syi; std::vector<double> sll (narrow.size ());
         for (size_t p : narrow) { sxi.push_back (xi[p]); syi.push_back (yi[p]); }
-        QG_TRY (qg_forward (ctx, cfg, narrow.size (), sxi.data (), syi.data (), sll.data ()));
+        const qg_env_reuse saved = g_env_reuse;
+        g_env_reuse.keep = nullptr; g_env_reuse.src = &er; g_env_reuse.pick = &narrow;
+        const int rc = qg_forward (ctx, cfg, narrow.size (), sxi.data (), syi.data (), sll.data ());
+        g_env_reuse = saved;
+        QG_TRY (rc);
         for (size_t q = 0; q < narrow.size (); ++q) loglike[narrow[q]] = sll[q];
       }
       return QG_OK;
+    }
+    if (!ctx->fb_exact) {
+      // probability-space kernels for the pairs whose runs fit one warp, log-space kernels for the others (see qg_pair_is_multiwarp)
+      std::vector<size_t> part[2];
+      for (size_t p = 0; p < n_pairs; ++p) part[qg_pair_is_multiwarp (er, p) ? 1 : 0].push_back (p);
+      if (!part[0].empty () && !part[1].empty ()) {
+        for (int c = 0; c < 2; ++c) {
+          std::vector<uint32_t> sxi, syi; std::vector<double> sll (part[c].size ());
+          for (size_t p : part[c]) { sxi.push_back (xi[p]); syi.push_back (yi[p]); }
+          const qg_env_reuse saved = g_env_reuse;
+          g_env_reuse.keep = nullptr; g_env_reuse.src = &er; g_env_reuse.pick = &part[c];
+          const int rc = qg_forward (ctx, cfg, part[c].size (), sxi.data (), syi.data (), sll.data ());
+          g_env_reuse = saved;
+          QG_TRY (rc);
+          for (size_t q = 0; q < part[c].size (); ++q) loglike[part[c][q]] = sll[q];
+        }
+        return QG_OK;
+      }
     }
   }
   qg_dp_plan plan;
@@ -1669,12 +1700,20 @@ extern "C" int qg_backward_counts (qg_ctx* ctx, const qg_dpconfig* cfg, size_t n
   {
     // pairs with runs too wide for one CTA take the tiled path (qg_tile.cuh: log space, every Forward cell kept); the
     // others go through this function again on their own, with the envelopes already computed
-    std::vector<size_t> wide, narrow;
-    for (size_t p = 0; p < n_pairs; ++p) (qg_pair_is_wide (er, p) ? wide : narrow).push_back (p);
-    if (!wide.empty () && hook) return QG_RETRY_TWO_PASS;
-    if (!wide.empty ()) {
+    // (pairs whose runs need several warps but fit one CTA: log-space kernels; the rest of a mixed call keeps the probability-space ones)
+    std::vector<size_t> wide, part[2];
+    for (size_t p = 0; p < n_pairs; ++p) {
+      if (qg_pair_is_wide (er, p)) wide.push_back (p);
+      else part[(!ctx->fb_exact && qg_pair_is_multiwarp (er, p)) ? 1 : 0].push_back (p);
+    }
+    const bool mixed = !part[0].empty () && !part[1].empty ();
+    if ((!wide.empty () || mixed) && hook) return QG_RETRY_TWO_PASS;
+    if (!wide.empty () || mixed) {
       std::vector<double> sum (nC, 0.0);
-      if (!narrow.empty ()) {
+      for (int cls = 0; cls < 2; ++cls) {
+        const std::vector<size_t>& narrow = part[cls];
+        if (narrow.empty ()) continue;
+        std::vector<double> csum (nC, 0.0);
         std::vector<uint32_t> nx (narrow.size ()), ny (narrow.size ());
         std::vector<double> nw (narrow.size (), 1.0), nf (narrow.size ()), nb (narrow.size ()), npp;
         for (size_t q = 0; q < narrow.size (); ++q) { nx[q] = xi[narrow[q]]; ny[q] = yi[narrow[q]]; if (weights) nw[q] = weights[narrow[q]]; }
@@ -1682,17 +1721,20 @@ extern "C" int qg_backward_counts (qg_ctx* ctx, const qg_dpconfig* cfg, size_t n
         const qg_env_reuse saved = g_env_reuse;
         g_env_reuse.keep = nullptr; g_env_reuse.src = &er; g_env_reuse.pick = &narrow;
         const int rc = qg_backward_counts (ctx, cfg, narrow.size (), nx.data (), ny.data (), weights ? nw.data () : nullptr, nf.data (), nb.data (),
-                                           sum.data (), counts_per_pair ? npp.data () : nullptr);
+                                           csum.data (), counts_per_pair ? npp.data () : nullptr);
         g_env_reuse = saved;
         QG_TRY (rc);
+        for (uint64_t k = 0; k < nC; ++k) sum[k] += csum[k];
         for (size_t q = 0; q < narrow.size (); ++q) {
           if (fwd_loglike) fwd_loglike[narrow[q]] = nf[q];
           if (back_loglike) back_loglike[narrow[q]] = nb[q];
           if (counts_per_pair) memcpy (counts_per_pair + (uint64_t) narrow[q] * nC, npp.data () + q * nC, sizeof (double) * nC);
         }
       }
-      qg_wide_fb fb; fb.weights = weights; fb.back = back_loglike; fb.counts_sum = sum.data (); fb.counts_per_pair = counts_per_pair; fb.nC = nC;
-      QG_TRY (qg_wide_run (ctx, cfg, er, wide, xi, yi, 2, nullptr, fwd_loglike, nullptr, nullptr, nullptr, &fb));
+      if (!wide.empty ()) {
+        qg_wide_fb fb; fb.weights = weights; fb.back = back_loglike; fb.counts_sum = sum.data (); fb.counts_per_pair = counts_per_pair; fb.nC = nC;
+        QG_TRY (qg_wide_run (ctx, cfg, er, wide, xi, yi, 2, nullptr, fwd_loglike, nullptr, nullptr, nullptr, &fb));
+      }
       if (counts_sum) memcpy (counts_sum, sum.data (), sizeof (double) * nC);
       QG_CUDA (ctx, qg_sync (ctx));
       return QG_OK;

@@ -259,3 +259,17 @@ def test_emu_pool_matches_single_context(emu, emu_lib, oracle):
         assert abs(e1["loglike"] - e2["loglike"]) <= 1e-12 * abs(e1["loglike"])
     finally:
         P.close()
+
+
+def test_emu_forward_backward_kernel_choice_per_pair(emu, oracle, workload):
+    """a call whose pairs need different kernels (bands wider than 256 diagonals next to narrow runs) is split per pair:
+    probability-space kernels for the pairs that fit one warp, log-space ones for the others -- each within its tolerance,
+    whatever its batch-mates are"""
+    x, reads, s_or = workload
+    xi, yi = pc.all_pairs(len(x), len(reads))
+    cfg = api.dp_config(kmer_threshold=6, band_size=300)
+    d, _ = emu.envelopes(cfg, xi, yi, cell_size=48)
+    widths = [len(v) for v in d]
+    assert min(widths) <= 256 < max(widths), widths                # both kinds present
+    pc.check_forward(emu, oracle, x, reads, s_or, cfg, xi, yi, exact=False)
+    pc.check_backward(emu, oracle, x, reads, s_or, cfg, xi, yi, exact=False)

@@ -256,3 +256,21 @@ def test_empty_pair_lists_are_noops(gpu, oracle, workload):
     assert np.all(np.asarray(b["counts"]) == 0) if "counts" in b else True
     a = gpu.align_reads(cfg, np.zeros(0), first=0, count=0)
     assert len(a["score"]) == 0
+
+
+def test_forward_backward_kernel_choice_per_pair(gpu, oracle, workload):
+    """a call whose pairs need different kernels (bands wider than 256 diagonals next to narrow runs) is split per pair:
+    probability-space kernels for the pairs that fit one warp, log-space ones for the others -- each within its tolerance,
+    whatever its batch-mates are; the E-step on top of such a call takes its two-pass form"""
+    x, reads, s_or = workload
+    xi, yi = pc.all_pairs(len(x), len(reads))
+    cfg = api.dp_config(kmer_threshold=14, band_size=300)
+    d, _ = gpu.envelopes(cfg, xi, yi, cell_size=48)
+    widths = [len(v) for v in d]
+    assert min(widths) <= 256 < max(widths), widths
+    pc.check_forward(gpu, oracle, x, reads, s_or, cfg, xi, yi, exact=False)
+    pc.check_backward(gpu, oracle, x, reads, s_or, cfg, xi, yi, exact=False)
+    from quaff_b200.params import QuaffNullParams
+    nullp = QuaffNullParams.load(os.path.join(os.path.dirname(__file__), "golden", "testquaffnullparams.json"))
+    pc.check_estep(gpu, oracle, x, reads, s_or, nullp, cfg, n_iter=1, exact=False)
+    gpu.set_fb_exact(True)
