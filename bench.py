@@ -381,6 +381,11 @@ def run_train(args):
     qp, nullp = load_models()
     G = api.QuaffGPU(device=local)
     G.set_refs(x); G.set_params(qp)
+    # the timed E-steps go through the native pool (qg_pool_estep): `--contexts` contexts on this rank's GPU, each with a
+    # contiguous range of the step's reads, so that one context's host work overlaps the other's kernels
+    n_ctx = args.contexts if args.contexts != 4 else 2
+    P = api.QuaffPool(devices=[local], contexts_per_device=n_ctx)
+    P.set_refs(x); P.set_params(qp)
     cfg = api.dp_config(kmer_threshold=20, band_size=64, kmer_len=6)
     null_ll = [np.array([api.null_loglike(nullp, r, G.L) for r in b]) for b in batches]
 
@@ -410,8 +415,7 @@ def run_train(args):
 
     def step(i, timed=False):
         b = i % POOL_BATCHES
-        G.set_seqs_raw(api.QG_READS, *flat[b])                    # the step's reads go up from host memory every step
-        r = G.estep(cfg, True, null_ll[b])
+        r = P.estep_raw(cfg, True, *flat[b], null_ll=null_ll[b])    # the step's reads go up from host memory every step
         ev0.record()
         counts, ll = allreduce_counts(r["counts"], r["loglike"])
         ev1.record(); ev1.synchronize()
@@ -421,13 +425,14 @@ def run_train(args):
     for i in range(args.warmup):
         step(i)
     sampler = ClockSampler(local); sampler.start()
-    G.stats(reset=True)
+    P.stats(reset=True)
     barrier(); t0 = time.perf_counter()
     for i in range(args.steps):
         counts, ll = step(args.warmup + i, True)
     barrier(); t1 = time.perf_counter()
     clocks = sampler.stop()
-    st = G.stats()
+    sts = P.stats()
+    st = {k: (sum(s_[k] for s_ in sts) if not k.startswith("ms_") else sum(s_[k] for s_ in sts) / len(sts)) for k in sts[0]}   # stage times: mean over the contexts (they overlap on the GPU)
     times = torch.tensor([t1 - t0, float(np.mean(ar_ms))], dtype=torch.float64, device="cuda")
     # Forward visits every envelope cell once; the Backward pass visits the gated pairs' cells again (cell_updates counts both)
     sums = torch.tensor([float(st["cell_updates"]), st["ms_forward"], st["ms_backward"], st["ms_seed"], float(st["kernel_launches"]), float(st["fwd_store_bytes"])],
@@ -443,7 +448,7 @@ def run_train(args):
             "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "train E-step over cfg4's reads: 8 kb reads vs 5 Mb reference, both strands, -kmatch 6 -kmatchn 20 -kmatchband 64, default params, "
                                    "fixed null model; Forward of every pair, Backward + counts of the gated pairs, one counts all-reduce per step",
-                       "reads_per_step_per_gpu": B, "ref_len": args.ref_len, "read_len": args.read_len,
+                       "reads_per_step_per_gpu": B, "ref_len": args.ref_len, "read_len": args.read_len, "contexts_per_gpu": n_ctx,
                        "collective": "all-reduce (sum) of %d doubles per step, %s" % (len(counts) + 1, "NCCL" if world > 1 else "single rank: no-op"),
                        "l2": "every step streams its own Forward checkpoints / row parameters, larger than L2; 2 read batches alternate"},
             "e2e": {"value": B * args.steps * world / dt, "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(8 * (len(counts) + 1 + B)),
@@ -460,7 +465,7 @@ def run_train(args):
             "loglike": ll,
         }
         print(json.dumps(line), flush=True)
-    G.close()
+    P.close(); G.close()
     if world > 1:
         dist.destroy_process_group()
 

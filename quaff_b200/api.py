@@ -606,8 +606,12 @@ class QuaffPool:
         return self.align_reads_raw(cfg, tok, qual, off, null_ll, chunk_reads)
 
     def estep(self, cfg: DPConfig, use_null: bool, reads: Sequence[FastSeq], null_ll: np.ndarray, sort_order: Optional[List[List[int]]] = None):
-        ny, nx = len(reads), self.n_refs
-        tok, qual, off = _flatten(reads, True)
+        return self.estep_raw(cfg, use_null, *_flatten(reads, True), null_ll=null_ll, sort_order=sort_order)
+
+    def estep_raw(self, cfg: DPConfig, use_null: bool, tok: np.ndarray, qual: np.ndarray, off: np.ndarray, null_ll: np.ndarray,
+                  sort_order: Optional[List[List[int]]] = None):
+        """seam C over host buffers (tokens, qualities, offsets of the whole read set)"""
+        ny, nx = len(off) - 1, self.n_refs
         so = np.zeros((ny, nx), dtype=np.uint32); sl = np.zeros(ny, dtype=np.uint32)
         for m in range(ny):
             o = list(range(nx)) if sort_order is None else sort_order[m]

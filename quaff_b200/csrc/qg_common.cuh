@@ -96,6 +96,7 @@ struct qg_segment {
   uint32_t xseq, yseq;               // sequence indices
   uint32_t nwarps;                   // warps cooperating on the segment (1 unless width > 32*R)
   uint32_t R;                        // diagonals per lane
+  uint32_t half;                     // Viterbi pointers of this segment are 16-bit words (R <= 4 nibbles: qg_vit_kernel), not 32-bit
   uint64_t trace_off;                // word offset of this segment's pointer block
   uint64_t store_off;                // double offset of this segment's stored Forward matrix
   uint64_t rp_off;                   // row offset of the read's row-parameter block

@@ -356,7 +356,8 @@ __global__ void qg_traceback_kernel (const qg_pair_dp* __restrict__ pairs, uint3
     }
     const int slot = d - sg.dlo, R = (int) sg.R;
     const int vl = slot / R, c = slot - vl * R;
-    const uint32_t word = trace[sg.trace_off + (uint64_t) (j + vl) * (32 * sg.nwarps) + vl];
+    const uint32_t word = sg.half ? (uint32_t) ((const uint16_t*) (trace + sg.trace_off))[(uint64_t) (j + vl) * 32 + vl]
+                                  : trace[sg.trace_off + (uint64_t) (j + vl) * (32 * sg.nwarps) + vl];
     const uint32_t nib = (word >> (4 * c)) & 15u;
     if (n >= pd.path_cap) { *err_flag = 2; break; }
     if (state == 1) {
@@ -420,10 +421,15 @@ qg_traceback_warp_kernel (const qg_pair_dp* __restrict__ pairs, uint32_t npairs,
     const bool multi = sg.nwarps != 1;                      // more than one warp, or a narrow segment (nwarps == 0): direct loads
     const bool narrow = sg.nwarps == 0;                     // one u32 per row, nibble = slot (qg_vit_narrow_kernel)
     if (!multi) {
+      // 32 loads in flight per lane either way: the word size is decided outside the loop
+      if (sg.half) {
+        const uint16_t* t16 = (const uint16_t*) (trace + sg.trace_off) + lane;
 #pragma unroll 8
-      for (int r = 0; r < 32; ++r) {
-        const int u = u_top - r;
-        s_tile[w][r][lane] = (u >= 0) ? trace[sg.trace_off + (uint64_t) u * 32 + lane] : 0u;
+        for (int r = 0; r < 32; ++r) { const int u = u_top - r; s_tile[w][r][lane] = (u >= 0) ? (uint32_t) t16[(uint64_t) u * 32] : 0u; }
+      } else {
+        const uint32_t* t32 = trace + sg.trace_off + lane;
+#pragma unroll 8
+        for (int r = 0; r < 32; ++r) { const int u = u_top - r; s_tile[w][r][lane] = (u >= 0) ? t32[(uint64_t) u * 32] : 0u; }
       }
     }
     __syncwarp ();

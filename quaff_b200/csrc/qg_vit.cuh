@@ -143,11 +143,18 @@ qg_vit_kernel (const qg_vit_args a) {
   if (1 - sg.dlo > f_lo) f_lo = 1 - sg.dlo;
   { const long long h = (long long) xlen - sg.dlo - (long long) (R - 1) * v_last - c_last; if (h < f_hi) f_hi = (int) h; }
   if (f_hi < f_lo) { f_lo = total + 1; f_hi = total; }      // no fast phase
-  uint32_t* tr = a.trace + sg.trace_off + L.vl;
   int u = 1;
-  for (; u < f_lo && u <= total; ++u) tr[(uint64_t) u * 32] = L.template step<true> (u);
-  for (; u <= f_hi; ++u) tr[(uint64_t) u * 32] = L.template step<false> (u);
-  for (; u <= total; ++u) tr[(uint64_t) u * 32] = L.template step<true> (u);
+  if (R <= 4) {                                             // 16-bit pointer words (segment flag `half`, set by the plan for exactly these kernels)
+    uint16_t* tr = (uint16_t*) (a.trace + sg.trace_off) + L.vl;
+    for (; u < f_lo && u <= total; ++u) tr[(uint64_t) u * 32] = (uint16_t) L.template step<true> (u);
+    for (; u <= f_hi; ++u) tr[(uint64_t) u * 32] = (uint16_t) L.template step<false> (u);
+    for (; u <= total; ++u) tr[(uint64_t) u * 32] = (uint16_t) L.template step<true> (u);
+  } else {
+    uint32_t* tr = a.trace + sg.trace_off + L.vl;
+    for (; u < f_lo && u <= total; ++u) tr[(uint64_t) u * 32] = L.template step<true> (u);
+    for (; u <= f_hi; ++u) tr[(uint64_t) u * 32] = L.template step<false> (u);
+    for (; u <= total; ++u) tr[(uint64_t) u * 32] = L.template step<true> (u);
+  }
 
   // segment result: max over end cells, ties -> largest i (qmodel.cpp:1568-1574)
   double bestEnd = L.bestEnd; int bestI = L.bestI;

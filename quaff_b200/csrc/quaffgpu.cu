@@ -825,6 +825,10 @@ static int qg_build_plan (qg_ctx* ctx, const qg_env_result& er, size_t p0, size_
       const bool narrow = mode == 0 && sg.width <= 4 && !getenv ("QG_VIT_GENERIC");    // one thread per run (qg_vit_narrow_kernel)
       if (narrow) { sg.R = sg.width; sg.nwarps = 0; sg.trace_off = plan.trace_words; plan.trace_words += (((uint64_t) pp.ylen + 4) / 4) * 4; }
       else if (diag_forward && (mode == 1 || mode == 2) && sg.width == 1) { sg.R = 1; sg.nwarps = 0; }   // isolated diagonal: one thread (qg_forward_prob_diag_kernel), closed-form Backward
+      else if (mode == 0 && nw == 1 && R <= 4 && !getenv ("QG_VIT_GENERIC")) {
+        // qg_vit_kernel<2..4>: R nibbles per lane fit a 16-bit word -- half the pointer bytes of the band (4 bit per slot)
+        sg.half = 1; sg.trace_off = plan.trace_words; plan.trace_words += (((uint64_t) pp.ylen + lanes + 1) * lanes + 1) / 2;
+      }
       else if (mode == 0 || mode == 3) { sg.trace_off = plan.trace_words; plan.trace_words += ((uint64_t) pp.ylen + lanes + 1) * lanes; }
       if (mode == 3) { sg.acc_off = plan.acc_rows; plan.acc_rows += (uint64_t) pp.ylen + 2; }
       if (mode == 2) { if (sg.nwarps != 0) { sg.store_off = plan.store_doubles; plan.store_doubles += ((uint64_t) pp.ylen + lanes + 1) * 3 * lanes * R; }
