@@ -136,7 +136,7 @@ def reference_cpu_run(n_reads: int, threads: int, ref_len: int = REF_LEN, read_l
             open(pj, "w").write(open(PARAMS_JSON).read()); open(nj, "w").write(open(NULL_JSON).read())      # the same text the GPU arm parsed
             cmd = [po.REF_QUAFF, "align", fa, fq, "-params", pj, "-null", nj, "-kmatchband", "64", "-format", "sam", "-threads", str(threads)]
             t0 = time.time()
-            res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+            res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, cwd=td)   # the reference CLI leaves a tempdir in its working directory
             dt = time.time() - t0
             if res.returncode != 0:
                 raise RuntimeError("reference quaff failed: " + res.stderr[-500:])
@@ -232,7 +232,7 @@ def run_cli(args):
         def run(fastq):
             t0 = time.time()
             with open(out_sam, "w") as fh:
-                res = subprocess.run([GPU_QUAFF, "align", fa, fastq] + base, stdout=fh, stderr=subprocess.PIPE, text=True,
+                res = subprocess.run([GPU_QUAFF, "align", fa, fastq] + base, stdout=fh, stderr=subprocess.PIPE, text=True, cwd=td,
                                      env=dict(os.environ, QUAFF_GPU_TRACE="1"))
             dt = time.time() - t0
             if res.returncode != 0:
@@ -339,7 +339,7 @@ def run_cfg5(args):
                     open(pj, "w").write(open(PARAMS_JSON).read()); open(nj, "w").write(open(NULL_JSON).read())
                     tc = time.time()
                     res = subprocess.run([po.REF_QUAFF, "align", fa, fq, "-params", pj, "-null", nj, "-kmatchoff", "-format", "sam", "-threads", "2"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+                                         stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, cwd=td)
                     secs = time.time() - tc
                 if res.returncode == 0:
                     from quaff_b200 import sam

@@ -13,6 +13,7 @@ import json
 import os
 import re
 import subprocess
+import tempfile
 
 import numpy as np
 import pytest
@@ -161,7 +162,7 @@ def _run(binary, args, env=None):
     e = dict(os.environ)
     if env:
         e.update(env)
-    res = subprocess.run([binary] + args, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=e, timeout=1200)
+    res = subprocess.run([binary] + args, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=e, timeout=1200, cwd=tempfile.gettempdir())
     assert res.returncode == 0, res.stderr[-800:]
     return res.stdout, res.stderr
 

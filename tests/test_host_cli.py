@@ -7,6 +7,7 @@ Both compare against oracle/_ref/quaff, the unmodified reference CLI; skipped wh
 (they need /root/reference at build time, but run anywhere)."""
 import os
 import subprocess
+import tempfile
 import sys
 
 import pytest
@@ -35,7 +36,7 @@ def _run(binary, args, env=None):
     e = dict(os.environ)
     if env:
         e.update(env)
-    res = subprocess.run([binary] + args, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=e, timeout=1200)
+    res = subprocess.run([binary] + args, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=e, timeout=1200, cwd=tempfile.gettempdir())
     assert res.returncode == 0, res.stderr[-800:]
     return res.stdout
 
