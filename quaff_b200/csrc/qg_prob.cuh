@@ -310,8 +310,11 @@ __global__ void qg_forward_prob_finalize_kernel (const qg_pair_dp* __restrict__ 
 }
 
 // ---- Backward + counts, probability space, pull form (see qg_backward.cuh for the structure) -------------------------
+#ifndef QG_BWD_MINB
+#define QG_BWD_MINB 12
+#endif
 template<int R>
-__global__ void __launch_bounds__ (32, 12)
+__global__ void __launch_bounds__ (32, QG_BWD_MINB)
 qg_backward_prob_kernel (const qg_prob_args a) {
   const qg_segment sg = a.segs[blockIdx.x];
   const int lane = threadIdx.x;
