@@ -11,6 +11,8 @@ LIB = os.path.join(HERE, "libquaffgpu_emu.so")
 
 
 def build(force=False):
+    if os.environ.get("QG_EMU_LIB"):                      # e.g. an AddressSanitizer build of the same sources
+        return os.environ["QG_EMU_LIB"]
     srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "cuda_emu.h"), os.path.join(HERE, "cuda_emu.cpp"),
                                                                  os.path.join(ROOT, "include", "quaffgpu.h")]
     if not force and os.path.exists(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(s) for s in srcs):
