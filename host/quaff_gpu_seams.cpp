@@ -468,9 +468,9 @@ void quaffGpuAlign (QuaffAligner& aligner, std::ostream& out, const vguard<FastS
 // ---- seam B -------------------------------------------------------------------------------------------------------
 void quaffGpuOverlap (QuaffOverlapAligner& aligner, std::ostream& out, const vguard<FastSeq>& seqs, size_t nOriginals,
                       const QuaffParams& params, const QuaffNullParams& nullModel, QuaffDPConfig& config) {
-  Gpu g;
+  // the scheduler's pair list over every device of -gpu (QUAFF_GPU_OVERLAP_CONTEXTS contexts on each, default 1)
+  GpuPool g ((int) std::max<size_t> (1, envSize ("QUAFF_GPU_OVERLAP_CONTEXTS", 1)));
   const Flat f = flatten (seqs, true);
-  g.ok (qg_set_seqs (g.ctx, QG_READS, seqs.size(), f.tok.data(), f.quals ? f.qual.data() : NULL, f.off.data()));
   const QuaffScores qs (params);
   const ScoreTables t = tables (qs);
   qg_overlap_model om;
@@ -478,14 +478,14 @@ void quaffGpuOverlap (QuaffOverlapAligner& aligner, std::ostream& out, const vgu
   for (int r = 0; r < 4; ++r) om.log_ref_base[r] = log (params.refBase[r]);
   om.begin_insert = params.beginInsert.data(); om.begin_delete = params.beginDelete.data();
   om.extend_insert = params.extendInsert; om.extend_delete = params.extendDelete;
-  g.ok (qg_set_overlap_model (g.ctx, &om));
   const qg_dpconfig gc = gpuConfig (config);
   // stored reverse strands: nullModel.logLikelihood (y.revcomp()) of the reference = the original read's
   std::vector<double> nullLL (seqs.size());
   for (size_t n = 0; n < seqs.size(); ++n)
     nullLL[n] = nullModel.logLikelihood (n >= nOriginals ? seqs[n].revcomp() : seqs[n]);
   size_t np = 0; uint32_t *xi = NULL, *yi = NULL, *co = NULL; double* score = NULL; uint8_t* path = NULL; uint64_t* off = NULL;
-  g.ok (qg_overlap_reads (g.ctx, &gc, nOriginals, nullLL.data(), &np, &xi, &yi, &score, &co, &path, &off));
+  g.ok (qg_pool_overlap_reads (g.pool, &gc, &om, seqs.size(), f.tok.data(), f.quals ? f.qual.data() : NULL, f.off.data(), nOriginals, nullLL.data(),
+                               &np, &xi, &yi, &score, &co, &path, &off));
   aligner.writeAlignmentHeader (out, seqs, false);
   for (size_t p = 0; p < np; ++p) {
     if (!(score[p] > -numeric_limits<double>::infinity())) continue;

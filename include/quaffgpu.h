@@ -228,6 +228,14 @@ int  qg_pool_estep (qg_pool* pool, const qg_dpconfig* cfg, int use_null, size_t 
                     const uint8_t* tok, const uint8_t* qual, const uint64_t* offsets, const double* null_loglike,
                     uint32_t* sort_order, uint32_t* sort_len, double* y_loglike, double* param_counts, double* loglike_sum);
 
+/* seam B over the pool: every context holds the whole read set and the overlap model; the scheduler's pair list is cut into
+ * contiguous ranges balanced by cells.  Outputs as qg_overlap_reads (library-allocated, pair order).                  */
+int  qg_pool_overlap_reads (qg_pool* pool, const qg_dpconfig* cfg, const qg_overlap_model* model,
+                            size_t n_seqs, const uint8_t* tok, const uint8_t* qual, const uint64_t* offsets,
+                            size_t n_originals, const double* null_loglike,
+                            size_t* n_pairs_out, uint32_t** xi_out, uint32_t** yi_out,
+                            double** score_out, uint32_t** coords4_out, uint8_t** path_out, uint64_t** path_offsets_out);
+
 /* ---- instrumentation ------------------------------------------------------------------------------ */
 typedef struct {
   double ms_seed, ms_envelope, ms_prep, ms_viterbi, ms_traceback, ms_forward, ms_backward, ms_overlap, ms_h2d, ms_d2h;

@@ -35,7 +35,7 @@ ABI_SYMBOLS = [
     "qg_backward_counts", "qg_align_reads", "qg_align_reads_range", "qg_estep", "qg_set_overlap_model", "qg_overlap_viterbi", "qg_overlap_rows",
     "qg_overlap_reads", "qg_get_stats",
     "qg_device_count", "qg_init_devices", "qg_pool_create", "qg_pool_destroy", "qg_pool_last_error", "qg_pool_size", "qg_pool_context", "qg_pool_set_refs",
-    "qg_pool_set_align_model", "qg_pool_set_option", "qg_pool_align_reads", "qg_pool_estep",
+    "qg_pool_set_align_model", "qg_pool_set_option", "qg_pool_align_reads", "qg_pool_estep", "qg_pool_overlap_reads",
 ]
 
 

@@ -169,4 +169,72 @@ extern "C" int qg_pool_estep (qg_pool* p, const qg_dpconfig* cfg, int use_null, 
   *loglike_sum = s;
   return QG_OK;
 }
+
+// seam B over the pool ("overlap: partition the pair list; all reads replicated; no collective"): every context holds
+// the whole read set and the overlap model; the scheduler's pair list (qoverlap.cpp:528-547) is cut into contiguous ranges
+// balanced by cells (x length x y length); outputs are concatenated in pair order, so they equal qg_overlap_reads'.
+extern "C" int qg_pool_overlap_reads (qg_pool* p, const qg_dpconfig* cfg, const qg_overlap_model* model,
+                                      size_t n_seqs, const uint8_t* tok, const uint8_t* qual, const uint64_t* offsets,
+                                      size_t n_originals, const double* null_loglike,
+                                      size_t* n_pairs_out, uint32_t** xi_out, uint32_t** yi_out,
+                                      double** score_out, uint32_t** coords4_out, uint8_t** path_out, uint64_t** path_offsets_out) {
+  if (!p || !cfg || !model || !offsets || !null_loglike || !n_pairs_out || !xi_out || !yi_out || !score_out || !coords4_out || !path_out || !path_offsets_out
+      || (n_seqs && !tok)) return QG_ERR_INVALID;
+  if (n_originals > n_seqs) { p->err = "n_originals exceeds the read set"; return QG_ERR_INVALID; }
+  std::vector<uint32_t> xi, yi; std::vector<uint8_t> yc;
+  std::vector<double> work;
+  for (size_t nx = 0; nx + 1 < n_originals; ++nx)
+    for (size_t ny = nx + 1; ny < n_seqs; ++ny) {
+      xi.push_back ((uint32_t) nx); yi.push_back ((uint32_t) ny); yc.push_back (ny >= n_originals ? 1 : 0);
+      work.push_back ((double) (offsets[nx + 1] - offsets[nx]) * (double) (offsets[ny + 1] - offsets[ny]));
+    }
+  const size_t np = xi.size ();
+  const int n = (int) p->ctx.size ();
+  std::vector<size_t> cut (n + 1, np);
+  cut[0] = 0;
+  { double total = 0; for (double w : work) total += w;
+    double acc = 0; size_t q = 0;
+    for (int w = 1; w < n; ++w) { const double want = total * w / n; while (q < np && acc < want) acc += work[q++]; cut[w] = q; } }
+  std::vector<std::vector<double> > sc (n); std::vector<std::vector<uint32_t> > co (n); std::vector<std::vector<uint64_t> > po (n);
+  std::vector<uint8_t*> pa (n, nullptr);
+  const int rc = qg_pool_run (p, [&] (int w) -> int {
+    const size_t q0 = cut[w], q1 = cut[w + 1], nq = q1 - q0;
+    if (!nq) return QG_OK;
+    qg_ctx* ctx = p->ctx[w];
+    QG_TRY (qg_set_seqs (ctx, QG_READS, n_seqs, tok, qual, offsets));
+    QG_TRY (qg_set_overlap_model (ctx, model));
+    sc[w].resize (nq); co[w].resize (4 * nq); po[w].resize (nq + 1);
+    return qg_overlap_viterbi (ctx, cfg, nq, xi.data () + q0, yi.data () + q0, yc.data () + q0, nullptr, sc[w].data (), co[w].data (), &pa[w], po[w].data ());
+  });
+  if (rc != QG_OK) { for (uint8_t* b : pa) free (b); return rc; }
+  uint64_t path_total = 0;
+  for (int w = 0; w < n; ++w) if (!po[w].empty ()) path_total += po[w].back ();
+  double* osc = (double*) malloc (sizeof (double) * (np + 1));
+  uint32_t* oco = (uint32_t*) malloc (sizeof (uint32_t) * 4 * (np + 1));
+  uint64_t* opo = (uint64_t*) malloc (sizeof (uint64_t) * (np + 2));
+  uint32_t* oxi = (uint32_t*) malloc (sizeof (uint32_t) * (np + 1));
+  uint32_t* oyi = (uint32_t*) malloc (sizeof (uint32_t) * (np + 1));
+  uint8_t* opa = (uint8_t*) malloc (path_total + 1);
+  if (!osc || !oco || !opo || !oxi || !oyi || !opa) {
+    free (osc); free (oco); free (opo); free (oxi); free (oyi); free (opa); for (uint8_t* b : pa) free (b);
+    p->err = "out of host memory"; return QG_ERR_INVALID;
+  }
+  uint64_t base = 0;
+  opo[0] = 0;
+  for (int w = 0; w < n; ++w) {
+    const size_t q0 = cut[w], nq = cut[w + 1] - q0;
+    for (size_t q = 0; q < nq; ++q) {
+      const size_t g = q0 + q;
+      double v = sc[w][q];
+      if (v > -INFINITY) { v -= null_loglike[xi[g]]; v -= null_loglike[yi[g]]; }     // scoreAdjustedAlignment, qoverlap.cpp:292-302
+      osc[g] = v; oxi[g] = xi[g]; oyi[g] = yi[g];
+      for (int t = 0; t < 4; ++t) oco[4 * g + t] = co[w][4 * q + t];
+      opo[g + 1] = base + po[w][q + 1];
+    }
+    if (nq) { if (po[w].back ()) memcpy (opa + base, pa[w], po[w].back ()); base += po[w].back (); }
+    free (pa[w]);
+  }
+  *n_pairs_out = np; *xi_out = oxi; *yi_out = oyi; *score_out = osc; *coords4_out = oco; *path_out = opa; *path_offsets_out = opo;
+  return QG_OK;
+}
 #endif

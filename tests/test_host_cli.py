@@ -85,7 +85,11 @@ def _compare_all(gpu_binary, tmp, sizes, kn, same_libm):
     b = _run(gpu_binary, ["train", fa, fq, "-kmatchn", str(kn), "-maxiter", "3", "-order", "1", "-gpu"], env={"QUAFF_GPU_EXACT": "1"})
     assert "beginInsert" in a
     if same_libm:
-        assert _strip_refbase(a) == _strip_refbase(b)                               # log-space kernels, same exp(): the same text
+        # log-space kernels, same exp(): normally the same text.  The count scatter uses FP64 atomics whose order varies from run
+        # to run (OS threads on the shim, warps on the device): last-bit differences in the counts, which the M-step's
+        # Newton / Brent iterations (stop on a 1e-4 relative test, negbinom.cpp:11-16) can carry into the 5th-6th digit
+        if _strip_refbase(a) != _strip_refbase(b):
+            _assert_params_close(a, b, 1e-4)
     else:
         # on the device exp() differs from glibc in the last bit, and the M-step's Newton / Brent iterations stop on a 1e-4
         # relative test (negbinom.cpp:11-16), so fitted values can move in the 5th-6th digit: hold the stated 1e-4 bar
@@ -98,6 +102,8 @@ def _compare_all(gpu_binary, tmp, sizes, kn, same_libm):
         a = _run(REFQ, ["overlap", fq2, "-kmatchn", str(kn)] + extra + ["-threads", "1"])
         b = _run(gpu_binary, ["overlap", fq2, "-kmatchn", str(kn)] + extra + ["-gpu"])
         assert a == b and len(a) > 0
+        b2 = _run(gpu_binary, ["overlap", fq2, "-kmatchn", str(kn)] + extra + ["-gpu"], env={"QUAFF_GPU_OVERLAP_CONTEXTS": "2"})
+        assert a == b2                                                             # the pair list split over two contexts (qg_pool_overlap_reads)
     # BASELINE config 1
     a = _run(REFQ, ["align", os.path.join(GOLD, "tiny.fasta"), os.path.join(GOLD, "tiny.fastq"), "-params", os.path.join(GOLD, "testquaffparams.json"),
                     "-null", os.path.join(GOLD, "testquaffnullparams.json"), "-threads", "1"])
