@@ -73,6 +73,10 @@ def _compare_all(gpu_binary, tmp, sizes, kn, same_libm):
         a = _run(REFQ, ["align", fa, fq, "-kmatchn", str(kn), "-format", fmt, "-threads", "1"])
         b = _run(gpu_binary, ["align", fa, fq, "-kmatchn", str(kn), "-format", fmt, "-gpu"])
         assert a == b and len(a) > 0, f"align -format {fmt} differs"
+    # chunks of two reads over two contexts (qg_pool_align_reads): worker-side formatting, output in read order
+    a = _run(REFQ, ["align", fa, fq, "-kmatchn", str(kn), "-format", "sam", "-threads", "1"])
+    b = _run(gpu_binary, ["align", fa, fq, "-kmatchn", str(kn), "-format", "sam", "-gpu"], env={"QUAFF_GPU_CHUNK": "2", "QUAFF_GPU_CONTEXTS": "2"})
+    assert a == b
     a = _run(REFQ, ["align", fa, fq, "-kmatchn", str(kn), "-printall", "-nothreshold", "-global", "-threads", "1"])
     b = _run(gpu_binary, ["align", fa, fq, "-kmatchn", str(kn), "-printall", "-nothreshold", "-global", "-gpu"])
     assert a == b
