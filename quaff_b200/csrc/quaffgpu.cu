@@ -99,6 +99,16 @@ static int qg_fetch (qg_ctx* ctx, void* dst, const void* src, size_t bytes) {
   ctx->h_pinned_used += need;
   return QG_OK;
 }
+// a malloc'd host buffer that is freed on every return path unless it is handed to the caller (release)
+struct qg_hostbuf {
+  uint8_t* p = nullptr;
+  ~qg_hostbuf () { free (p); }
+  uint8_t* release () { uint8_t* r = p; p = nullptr; return r; }
+  qg_hostbuf () = default;
+  qg_hostbuf (const qg_hostbuf&) = delete;
+  qg_hostbuf& operator= (const qg_hostbuf&) = delete;
+};
+
 static int qg_download (qg_ctx* ctx, void* dst, const void* src, size_t bytes) {
   QG_TRY (qg_fetch (ctx, dst, src, bytes));
   return qg_fetch_wait (ctx);
@@ -1269,7 +1279,8 @@ static int qg_viterbi_impl (qg_ctx* ctx, const qg_dpconfig* cfg, size_t n_pairs,
           sxi.push_back (xi[p]); syi.push_back (yi[p]); swant.push_back (want[p]);
         }
         std::vector<double> ssc (narrow.size ()); std::vector<uint32_t> sxs (narrow.size ()), sxe (narrow.size ()); std::vector<uint64_t> soff (narrow.size () + 1);
-        uint8_t* sp = nullptr;
+        qg_hostbuf sp_;
+        uint8_t*& sp = sp_.p;
         QG_TRY (qg_viterbi_impl (ctx, cfg, narrow.size (), sxi.data (), syi.data (), swant.data (), 0, ssc.data (), paths ? sxs.data () : nullptr,
                                  paths ? sxe.data () : nullptr, paths ? &sp : nullptr, paths ? soff.data () : nullptr, &sub));
         for (size_t q = 0; q < narrow.size (); ++q) {
@@ -1277,7 +1288,6 @@ static int qg_viterbi_impl (qg_ctx* ctx, const qg_dpconfig* cfg, size_t n_pairs,
           score[p] = ssc[q];
           if (paths) { xs[p] = sxs[q]; xe[p] = sxe[q]; per_pair[p].assign (sp + soff[q], sp + soff[q + 1]); }
         }
-        free (sp);
       }
       if (paths) {
         // group mode: keep the best pair of each group only
@@ -1302,7 +1312,8 @@ static int qg_viterbi_impl (qg_ctx* ctx, const qg_dpconfig* cfg, size_t n_pairs,
   size_t freeb = 0, totb = 0;
   QG_CUDA (ctx, cudaMemGetInfo (&freeb, &totb));
   const uint64_t budget = (uint64_t) qg_env_size ("QG_TRACE_BUDGET_MB", std::min<size_t> (freeb / 2, (size_t) 32 << 30) >> 20) << 20;
-  uint8_t* all_paths = nullptr;                              // grows by realloc: no zero fill, handed to the caller at the end
+  qg_hostbuf all_paths_;                                     // grows by realloc: no zero fill, handed to the caller at the end, freed on any error return
+  uint8_t*& all_paths = all_paths_.p;
   std::vector<uint64_t> offs (n_pairs + 1, 0);
   uint64_t path_total = 0;
   const size_t step = group ? group : 1;
@@ -1419,7 +1430,7 @@ static int qg_viterbi_impl (qg_ctx* ctx, const qg_dpconfig* cfg, size_t n_pairs,
                    ctx->scratch[SC_OUT3].as<uint32_t> (), ctx->scratch[SC_MISC1].as<uint64_t> (), ctx->scratch[SC_PATHOUT].as<uint8_t> ());
         QG_TRY (qg_check_launch (ctx, "qg_path_gather_kernel"));
         uint8_t* grown = (uint8_t*) realloc (all_paths, path_total + goff[np] + 1);
-        if (!grown) { free (all_paths); QG_FAIL (ctx, QG_ERR_INVALID, "out of host memory"); }
+        if (!grown) QG_FAIL (ctx, QG_ERR_INVALID, "out of host memory");
         all_paths = grown;
         QG_TRY (qg_download (ctx, all_paths + path_total, ctx->scratch[SC_PATHOUT].p, goff[np]));
       }
@@ -1432,7 +1443,7 @@ static int qg_viterbi_impl (qg_ctx* ctx, const qg_dpconfig* cfg, size_t n_pairs,
     memcpy (path_offsets, offs.data (), sizeof (uint64_t) * (n_pairs + 1));
     if (!all_paths) all_paths = (uint8_t*) malloc (1);
     if (!all_paths) QG_FAIL (ctx, QG_ERR_INVALID, "out of host memory");
-    *path_out = all_paths;
+    *path_out = all_paths_.release ();
   }
   return QG_OK;
 }
