@@ -274,3 +274,31 @@ def test_forward_backward_kernel_choice_per_pair(gpu, oracle, workload):
     nullp = QuaffNullParams.load(os.path.join(os.path.dirname(__file__), "golden", "testquaffnullparams.json"))
     pc.check_estep(gpu, oracle, x, reads, s_or, nullp, cfg, n_iter=1, exact=False)
     gpu.set_fb_exact(True)
+
+
+def test_pool_matches_single_context(gpu, oracle):
+    """qg_pool_*: chunks of reads over three contexts on the device (host threads inside the library), results in read order;
+    E-step count sum over contiguous read ranges -- both against the single-context entry points"""
+    from quaff_b200.params import QuaffNullParams
+    x, reads = pc.make_workload(ref_len=40000, n_reads=11, read_len=1200, seed=31)
+    qp = pc.default_params()
+    nullp = QuaffNullParams.load(os.path.join(os.path.dirname(__file__), "golden", "testquaffnullparams.json"))
+    cfg = api.dp_config(kmer_threshold=14)
+    null_ll = np.array([api.null_loglike(nullp, r, gpu.L) for r in reads])
+    gpu.set_refs(x); gpu.set_reads(reads); gpu.set_params(qp)
+    one = gpu.align_reads(cfg, null_ll, split_paths=False)
+    P = api.QuaffPool(devices=[0], contexts_per_device=3)
+    try:
+        assert P.size() == 3
+        P.set_refs(x); P.set_params(qp)
+        many = P.align_reads(cfg, reads, null_ll, chunk_reads=2)          # 6 chunks over 3 contexts
+        for k in ("best_ref", "score", "x_start", "x_end", "paths", "path_offsets"):
+            assert np.array_equal(np.asarray(one[k]), np.asarray(many[k])), k
+        gpu.set_fb_exact(True); P.set_fb_exact(True)
+        e1 = gpu.estep(cfg, True, null_ll)
+        e2 = P.estep(cfg, True, reads, null_ll)
+        assert e1["sort_order"] == e2["sort_order"] and np.array_equal(e1["y_loglike"], e2["y_loglike"])
+        np.testing.assert_allclose(e2["counts"], e1["counts"], rtol=1e-12, atol=1e-300)
+        assert abs(e1["loglike"] - e2["loglike"]) <= 1e-12 * abs(e1["loglike"])
+    finally:
+        P.close()
