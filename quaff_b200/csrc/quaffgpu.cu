@@ -866,11 +866,24 @@ static int qg_build_plan (qg_ctx* ctx, const qg_env_result& er, size_t p0, size_
   return QG_OK;
 }
 
+// Launch classes run concurrently on side streams, but every CTA is one long dependent chain and the biggest class alone nearly
+// fills the resident-CTA slots: a small class launched after it waits for a slot and then adds a whole chain to the stage's
+// time.  Small classes first: they take their few slots at once and the big class fills the rest.
+template<class LaunchVec>
+static std::vector<size_t> qg_launch_order (const LaunchVec& launches) {
+  std::vector<size_t> order (launches.size ());
+  std::iota (order.begin (), order.end (), (size_t) 0);
+  if (!getenv ("QG_LAUNCH_PLAN_ORDER"))
+    std::stable_sort (order.begin (), order.end (), [&] (size_t u, size_t v) { return launches[u].count < launches[v].count; });
+  return order;
+}
+
 template<int MODE>
 static int qg_launch_fill (qg_ctx* ctx, const qg_dp_plan& plan, qg_fill_args a, const qg_segment* d_segs_launch_order) {
   QG_TRY (qg_fork (ctx));
   int kcls = 0;
-  for (const auto& L : plan.launches) {
+  for (size_t li : qg_launch_order (plan.launches)) {
+    const auto& L = plan.launches[li];
     cudaStream_t st; QG_TRY (qg_side (ctx, kcls++, &st));
     a.segs = d_segs_launch_order + L.begin;
     if (L.nw == 0) {                                        // narrow Viterbi segments, one thread each
@@ -1545,7 +1558,8 @@ template<int BACKWARD>
 static int qg_launch_prob (qg_ctx* ctx, const qg_dp_plan& plan, qg_prob_args a, const qg_segment* d_segs_launch_order) {
   QG_TRY (qg_fork (ctx));
   int kcls = 0;
-  for (const auto& L : plan.launches) {
+  for (size_t li : qg_launch_order (plan.launches)) {
+    const auto& L = plan.launches[li];
     cudaStream_t st; QG_TRY (qg_side (ctx, kcls++, &st));
     a.segs = d_segs_launch_order + L.begin;
     if (L.nw == 0) {                                        // isolated diagonals: one thread each (Forward), closed form (Backward)
