@@ -868,7 +868,8 @@ static int qg_build_plan (qg_ctx* ctx, const qg_env_result& er, size_t p0, size_
 
 // Launch classes run concurrently on side streams, but every CTA is one long dependent chain and the biggest class alone nearly
 // fills the resident-CTA slots: a small class launched after it waits for a slot and then adds a whole chain to the stage's
-// time.  Small classes first: they take their few slots at once and the big class fills the rest.
+// time.  Small classes first: they take their few slots at once and the big class fills the rest (Viterbi fill of 1536 reads:
+// 15.2 -> 14.1 ms).
 template<class LaunchVec>
 static std::vector<size_t> qg_launch_order (const LaunchVec& launches) {
   std::vector<size_t> order (launches.size ());
@@ -1558,8 +1559,7 @@ template<int BACKWARD>
 static int qg_launch_prob (qg_ctx* ctx, const qg_dp_plan& plan, qg_prob_args a, const qg_segment* d_segs_launch_order) {
   QG_TRY (qg_fork (ctx));
   int kcls = 0;
-  for (size_t li : qg_launch_order (plan.launches)) {
-    const auto& L = plan.launches[li];
+  for (const auto& L : plan.launches) {                   // plan order: small-first (qg_launch_order) measured no gain for these kernels
     cudaStream_t st; QG_TRY (qg_side (ctx, kcls++, &st));
     a.segs = d_segs_launch_order + L.begin;
     if (L.nw == 0) {                                        // isolated diagonals: one thread each (Forward), closed form (Backward)
